@@ -1,0 +1,170 @@
+/* rtb200.h — C ABI of the B200-native render path.
+ *
+ * This is the drop-in boundary for ONE hot path of dps/rust-raytracer: the timed
+ * region of `pub fn render(filename, scene)` (reference raytracer/src/raytracer.rs:250-266,
+ * precisely lines 259-263: the rayon `into_par_iter().for_each(render_line)` over row bands).
+ * The reference has no FFI; the contract of that region is
+ *     "given an immutable parsed scene, fill a caller-owned w*h*3 RGB8 row-major buffer, top row first".
+ * A Rust maintainer binds these entry points with an `extern "C"` block and calls
+ * rtb200_render_rgb8() in place of raytracer.rs:259-263.
+ *
+ * Conventions
+ *   - every struct is POD, little-endian, caller-owned and read-only for the callee;
+ *   - the callee copies what it needs before returning; no callee allocation escapes
+ *     except opaque handles released with the matching *_release call;
+ *   - every function returns 0 on success, a negative rt_status otherwise, and
+ *     rtb200_last_error() then returns a thread-local message (the reference panics instead);
+ *   - calls are blocking; one caller thread at a time per process;
+ *   - there is NO CPU fallback: without a CUDA device / the sm_100a kernels every render call fails.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB200_ABI_VERSION 1
+
+/* ---- scene records (reference types flattened) --------------------------------------------- */
+
+/* Point3D {x,y,z: f64} — raytracer/src/point3d.rs:10-15 */
+typedef struct { double x, y, z; } rt_vec3;
+
+/* The four computed fields of Camera that get_ray uses — raytracer/src/camera.rs:12-21,79-84.
+ * Fill with rtb200_camera_from_params() (= Camera::new, camera.rs:45-77). */
+typedef struct { rt_vec3 origin, lower_left_corner, horizontal, vertical; } rt_camera;
+
+/* CameraParams — raytracer/src/camera.rs:29-36 (the JSON form of the camera) */
+typedef struct { rt_vec3 look_from, look_at, vup; double vfov_deg, aspect; } rt_camera_params;
+
+/* Material variants — raytracer/src/materials.rs:35-42 */
+enum rt_material_kind {
+    RT_LAMBERTIAN = 0, /* materials.rs:73-95   albedo                              */
+    RT_METAL      = 1, /* materials.rs:99-129  albedo, param = fuzz                */
+    RT_GLASS      = 2, /* materials.rs:132-199 param = index_of_refraction         */
+    RT_TEXTURE    = 3, /* materials.rs:203-267 texture index, param = h_offset     */
+    RT_LIGHT      = 4  /* materials.rs:57-69                                       */
+};
+
+/* Sphere {center, radius, material} — raytracer/src/sphere.rs:18-23. radius may be negative
+ * (hollow glass shell, data/test_scene.json:137). List ORDER is semantic: hit_world keeps the
+ * first sphere on equal t (raytracer.rs:52-56) and lights are visited in list order (raytracer.rs:103). */
+typedef struct {
+    rt_vec3  center;
+    double   radius;
+    uint32_t kind;        /* enum rt_material_kind */
+    float    albedo[3];   /* Srgb<f32>; ignored for Glass/Light; ignored for Texture (materials.rs:264) */
+    double   param;       /* fuzz | index_of_refraction | h_offset */
+    int32_t  texture;     /* index into rt_scene.textures for RT_TEXTURE, else -1 */
+    int32_t  reserved;
+} rt_sphere;
+
+/* Decoded RGB8 image, row-major, 3 B/texel. For Texture materials width/height are the values
+ * written in the JSON, NOT the decoded file's (materials.rs:208-209 with loader result .0 only, :32). */
+typedef struct { const uint8_t* rgb8; uint64_t width, height; } rt_image;
+
+/* Sky — raytracer/src/config.rs:22-28 and the miss branch raytracer.rs:134-163 */
+enum rt_sky_mode { RT_SKY_NONE = 0 /* black */, RT_SKY_GRADIENT = 1, RT_SKY_TEXTURE = 2 };
+typedef struct { uint32_t mode; uint32_t reserved; rt_image tex; } rt_sky;
+
+/* Config — raytracer/src/config.rs:66-75, plus the seed (the reference draws from an OS-seeded
+ * thread_rng and is not reproducible; see DESIGN.md "RNG contract"). */
+typedef struct {
+    uint32_t width, height, samples_per_pixel, max_depth;
+    rt_camera camera;
+    rt_sky    sky;
+    const rt_sphere* spheres;  uint64_t n_spheres;
+    const rt_image*  textures; uint64_t n_textures;
+    uint64_t seed;
+} rt_scene;
+
+/* ---- execution options and results ---------------------------------------------------------- */
+
+enum rt_trace_variant {
+    RT_VARIANT_AUTO      = 0,
+    RT_VARIANT_FILTERED  = 1, /* f32 conservative filter + exact f64 confirmation (default)   */
+    RT_VARIANT_EXACT_F64 = 2  /* every sphere tested in f64 (validation of the filter)        */
+};
+
+/* Which rows this call renders. Row-band b (band_rows consecutive rows) belongs to shard
+ * (b mod world). world=1 renders everything. Output buffers of a shard call are COMPACT: the
+ * shard's rows in increasing y, see rtb200_shard_rows(). */
+typedef struct {
+    int32_t  device;      /* CUDA ordinal; -1 = current device */
+    int32_t  rank, world; /* shard of the image rendered by this call */
+    uint32_t band_rows;   /* rows per interleaved band; 0 = default (1) */
+    uint32_t variant;     /* enum rt_trace_variant */
+    uint32_t flags;       /* reserved, must be 0 */
+    uint64_t sample_buffer_bytes; /* cap for the per-sample radiance staging buffer; 0 = default */
+} rt_options;
+
+typedef struct {
+    uint64_t rays;          /* hit_world invocations (primary + scattered + shadow), raytracer.rs:83 */
+    uint64_t samples;       /* camera samples traced */
+    uint64_t candidates;    /* f64-confirmed sphere tests (diagnostic) */
+    double   device_ms;     /* CUDA-event time of all kernels of this call on the launching stream */
+    double   trace_ms;      /* the trace kernel(s) alone */
+    double   wall_ms;       /* host wall time of the call, copies included */
+    uint32_t kernel_launches;
+    uint32_t batches;
+    uint64_t h2d_bytes, d2h_bytes;
+} rt_stats;
+
+enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,     /* bad argument / inconsistent scene */
+    RT_ERR_NO_DEVICE = -2,   /* no CUDA device or not sm_100 */
+    RT_ERR_CUDA = -3,        /* CUDA runtime failure (message has the detail) */
+    RT_ERR_UNSUPPORTED = -4, /* scene needs a feature this build lacks */
+    RT_ERR_OOM = -5
+};
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+int rtb200_abi_version(void);
+const char* rtb200_last_error(void);
+
+/* Camera::new — camera.rs:45-77 (host, f64, once per frame). */
+int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out);
+
+/* Number of rows of `height` that shard `rank` of `world` owns with the given band size. */
+uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_t band_rows);
+
+/* Replaces raytracer.rs:259-263 (+ the Vec<u8> it fills, :254): host scene in, host RGB8 out.
+ * Uploads the scene, renders on one GPU (opts==NULL) or the shard opts describes, copies back.
+ * out_rgb8: width*height*3 bytes (or shard_rows*width*3 when opts->world > 1). */
+int rtb200_render_rgb8(const rt_scene* scene, const rt_options* opts, uint8_t* out_rgb8, rt_stats* stats);
+
+/* Same path, but returns the per-pixel mean radiance BEFORE sqrt/quantisation (raytracer.rs:207-212
+ * computes sqrt(scale*sum)); used by parity tests. out_rgb: width*height*3 floats (or the shard's). */
+int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, float* out_rgb, rt_stats* stats);
+
+/* Resident form (scene stays in HBM between frames; output stays on the device). */
+typedef struct rtb200_scene_t* rtb200_scene_handle;
+int rtb200_scene_upload(const rt_scene* scene, const rt_options* opts, rtb200_scene_handle* out);
+/* dev_rgb8 / dev_linear_f32 are DEVICE pointers (either may be NULL); stream is a cudaStream_t or NULL. */
+int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream, rt_stats* stats);
+int rtb200_scene_release(rtb200_scene_handle h);
+
+/* Device-function probes: run the kernel's own device routines on one thread and return the result,
+ * so the reference's known-answer tests can be asserted against the GPU code itself.
+ *   sphere.rs:81-88, materials.rs:157-174, raytracer.rs:167-189, camera.rs:105-122 */
+int rtb200_probe_sphere_hit(const rt_vec3* center, double radius, const rt_vec3* origin, const rt_vec3* dir,
+                            double t_min, double t_max, int32_t* hit, double* t, rt_vec3* point, rt_vec3* normal,
+                            int32_t* front_face);
+int rtb200_probe_refract(const rt_vec3* uv, const rt_vec3* n, double etai_over_etat, rt_vec3* out);
+int rtb200_probe_reflectance(double cosine, double ref_idx, double* out);
+int rtb200_probe_sky(const rt_vec3* dir, uint32_t sky_mode, float out_rgb[3]);
+int rtb200_probe_get_ray(const rt_camera* cam, double u, double v, rt_vec3* origin, rt_vec3* dir);
+/* n uniform draws of the per-(pixel,sample) stream: kind 0 = gen::<f64>() in [0,1), 1 = gen_range(-1.0..1.0) */
+int rtb200_probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t kind, uint32_t n, double* out);
+/* u8 quantisation of raytracer.rs:207-213 for n linear means */
+int rtb200_probe_quantise(const float* mean_linear, uint32_t n, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,521 @@
+// rtb200_api.cu — the C ABI of include/rtb200.h: scene staging into HBM, batch scheduling of the trace /
+// resolve kernels, device<->host copies and error reporting. No CPU render path exists in this library.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtb200_kernels.cuh"
+
+using namespace rtk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RT_ERR_NO_DEVICE
+           : (e == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA);
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+struct GrowBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+};
+
+// Per-device execution context: one stream, grow-only work buffers, timing events. One render at a time.
+struct DeviceCtx {
+    bool init = false;
+    int device = -1;
+    int sm_count = 0;
+    size_t max_smem = 0;
+    cudaStream_t stream = nullptr;
+    GrowBuf samplebuf, accum, stack, small, out_rgb8, out_lin, probe;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+DeviceCtx g_ctx[64];
+
+int get_ctx(int device, DeviceCtx** out) {
+    if (device < 0) {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    }
+    if (device >= 64) return fail(RT_ERR_INVALID, "device ordinal out of range");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (device >= count) return fail(RT_ERR_NO_DEVICE, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    DeviceCtx& c = g_ctx[device];
+    if (!c.init) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+            return fail(RT_ERR_NO_DEVICE, buf);
+        }
+        c.device = device;
+        c.sm_count = prop.multiProcessorCount;
+        c.max_smem = prop.sharedMemPerBlockOptin;
+        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&c.ev_begin));
+        CU(cudaEventCreate(&c.ev_end));
+        c.init = true;
+    }
+    *out = &c;
+    return RT_OK;
+}
+
+struct V3 { double x, y, z; };
+inline V3 v3(const rt_vec3& a) { return V3{a.x, a.y, a.z}; }
+inline V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, double s) { return V3{a.x * s, a.y * s, a.z * s}; }
+inline double vlen(V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3 vunit(V3 a) { double l = vlen(a); return V3{a.x / l, a.y / l, a.z / l}; }
+inline V3 vcross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline rt_vec3 rv(V3 a) { return rt_vec3{a.x, a.y, a.z}; }
+
+float f32_up(double x) {   // smallest float >= x
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+}  // namespace
+
+struct rtb200_scene_t {
+    int device = -1;
+    DeviceCtx* ctx = nullptr;
+    TraceParams tp{};
+    rt_options opts{};
+    bool exact = false;
+    int grid = 0;
+    size_t smem = 0;
+    uint32_t spp_batch = 0;
+    std::vector<void*> owned;   // device allocations owned by the handle
+    uint64_t h2d_bytes = 0;
+};
+
+extern "C" {
+
+int rtb200_abi_version(void) { return RTB200_ABI_VERSION; }
+const char* rtb200_last_error(void) { return g_last_error.c_str(); }
+
+// Camera::new — camera.rs:45-77. Host, once per frame, f64, same operation order as the reference.
+// (Compiled with -fmad=false / no host contraction: see the Makefile.)
+int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out) {
+    if (!p || !out) return fail(RT_ERR_INVALID, "null argument");
+    const double PI = 3.14159265358979323846264338327950288;
+    double theta = p->vfov_deg * (PI / 180.0);
+    double half_height = std::tan(theta / 2.0);
+    double half_width = p->aspect * half_height;
+    V3 look_from = v3(p->look_from), look_at = v3(p->look_at), vup = v3(p->vup);
+    V3 w = vunit(look_from - look_at);
+    V3 u = vunit(vcross(vup, w));
+    V3 v = vcross(w, u);
+    V3 origin = look_from;
+    V3 llc = origin - (u * half_width) - (v * half_height) - w;
+    V3 horizontal = u * 2.0 * half_width;
+    V3 vertical = v * 2.0 * half_height;
+    out->origin = rv(origin); out->lower_left_corner = rv(llc); out->horizontal = rv(horizontal); out->vertical = rv(vertical);
+    return RT_OK;
+}
+
+uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_t band_rows) {
+    if (world <= 1) return height;
+    if (band_rows == 0) band_rows = 1;
+    uint32_t rows = 0;
+    for (uint32_t y = 0; y < height; ++y)
+        if ((int32_t)((y / band_rows) % (uint32_t)world) == rank) ++rows;
+    return rows;
+}
+
+int rtb200_scene_release(rtb200_scene_handle h) {
+    if (!h) return RT_OK;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return RT_OK;
+}
+
+static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** dev) {
+    *dev = nullptr;
+    if (bytes == 0) bytes = 16;
+    void* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    h->owned.push_back(d);
+    if (src) {
+        CU(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->ctx->stream));
+        h->h2d_bytes += bytes;
+    }
+    *dev = d;
+    return RT_OK;
+}
+
+int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
+    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rt_options opts{};
+    opts.device = -1; opts.rank = 0; opts.world = 1; opts.band_rows = 1; opts.variant = RT_VARIANT_AUTO;
+    if (opts_in) opts = *opts_in;
+    if (opts.world <= 0) opts.world = 1;
+    if (opts.band_rows == 0) opts.band_rows = 1;
+    if (opts.rank < 0 || opts.rank >= opts.world) return fail(RT_ERR_INVALID, "rank outside [0, world)");
+    if (opts.flags != 0) return fail(RT_ERR_INVALID, "flags must be 0");
+    if (s->width < 2 || s->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by w-1, h-1: raytracer.rs:199-200)");
+    if (s->samples_per_pixel == 0) return fail(RT_ERR_INVALID, "samples_per_pixel must be > 0");
+    if ((uint64_t)s->width * s->height >= (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
+    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
+    if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
+
+    uint32_t n = (uint32_t)s->n_spheres;
+    uint32_t n_lights = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const rt_sphere& sp = s->spheres[i];
+        if (sp.kind > RT_LIGHT) return fail(RT_ERR_INVALID, "unknown material kind");
+        if (sp.kind == RT_LIGHT) ++n_lights;
+        if (sp.kind == RT_TEXTURE) {
+            if (sp.texture < 0 || (uint64_t)sp.texture >= s->n_textures) return fail(RT_ERR_INVALID, "texture index out of range");
+            const rt_image& im = s->textures[sp.texture];
+            if (!im.rgb8 || im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "empty texture image");
+        }
+    }
+    if (n_lights > 0) return fail(RT_ERR_UNSUPPORTED, "Light materials (shadow-ray recursion, raytracer.rs:89-114) are not built yet");
+    if (s->sky.mode > RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "unknown sky mode");
+    if (s->sky.mode == RT_SKY_TEXTURE && (!s->sky.tex.rgb8 || s->sky.tex.width == 0 || s->sky.tex.height == 0))
+        return fail(RT_ERR_INVALID, "sky texture is empty");
+
+    DeviceCtx* ctx = nullptr;
+    int rc = get_ctx(opts.device, &ctx);
+    if (rc != RT_OK) return rc;
+
+    rtb200_scene_t* h = new rtb200_scene_t();
+    h->device = ctx->device; h->ctx = ctx; h->opts = opts;
+    h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
+    struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
+
+    // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
+    double g[3] = {0, 0, 0};
+    if (n) {
+        std::vector<double> tmp(n);
+        for (int c = 0; c < 3; ++c) {
+            for (uint32_t i = 0; i < n; ++i) tmp[i] = c == 0 ? s->spheres[i].center.x : (c == 1 ? s->spheres[i].center.y : s->spheres[i].center.z);
+            std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
+            g[c] = tmp[n / 2];
+            if (!std::isfinite(g[c])) g[c] = 0.0;
+        }
+    }
+
+    // ---- device records ----
+    const double U = 5.9604644775390625e-8;   // 2^-24
+    uint32_t n_pairs = (n + 1) / 2;
+    if (n_pairs == 0) n_pairs = 1;
+    std::vector<float> filt((size_t)n_pairs * 8);
+    std::vector<double> geo((size_t)std::max<uint32_t>(n, 1) * 4, 0.0);
+    std::vector<DevMat> mat(std::max<uint32_t>(n, 1));
+    memset(mat.data(), 0, mat.size() * sizeof(DevMat));
+    for (uint32_t pp = 0; pp < n_pairs; ++pp) {
+        for (int k = 0; k < 2; ++k) {
+            uint32_t i = 2 * pp + k;
+            float cx = 0.f, cy = 0.f, cz = 0.f, nk = -INFINITY;
+            if (i < n) {
+                const rt_sphere& sp = s->spheres[i];
+                double x = sp.center.x - g[0], y = sp.center.y - g[1], z = sp.center.z - g[2];
+                double c2 = x * x + y * y + z * z, r2 = sp.radius * sp.radius;
+                // candidate iff  b^2 + 2c.o - K - |o|^2 >= -(Es + Er):  nk = -K + Es rounded up
+                double Es = 96.0 * U * c2 + 16.0 * U * r2 + 1e-30;
+                double nkd = -(c2 - r2) + Es;
+                cx = (float)x; cy = (float)y; cz = (float)z;
+                nk = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
+                if (!(std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz))) { cx = cy = cz = 0.f; nk = INFINITY; }
+                geo[4 * (size_t)i + 0] = sp.center.x; geo[4 * (size_t)i + 1] = sp.center.y; geo[4 * (size_t)i + 2] = sp.center.z;
+                geo[4 * (size_t)i + 3] = sp.radius;
+                DevMat& m = mat[i];
+                m.kind = sp.kind; m.param = sp.param; m.tex = sp.texture; m.pad = 0;
+                if (sp.kind == RT_LAMBERTIAN || sp.kind == RT_METAL) { m.r = sp.albedo[0]; m.g = sp.albedo[1]; m.b = sp.albedo[2]; }
+                else { m.r = m.g = m.b = 1.0f; }   // Glass/Light attenuation is (1,1,1) (materials.rs:67,179); Texture uses texels
+            }
+            // layout: A = {cx0,cx1,cy0,cy1}, B = {cz0,cz1,nk0,nk1}
+            float* A = &filt[(size_t)pp * 8];
+            A[0 + k] = cx; A[2 + k] = cy; A[4 + k] = cz; A[6 + k] = nk;
+        }
+    }
+
+    TraceParams& tp = h->tp;
+    void* d = nullptr;
+    if ((rc = upload_array(h, filt.data(), filt.size() * 4, &d)) != RT_OK) return rc;
+    tp.filt = (const float4*)d;
+    if ((rc = upload_array(h, geo.data(), geo.size() * 8, &d)) != RT_OK) return rc;
+    tp.geo = (const double4*)d;
+    if ((rc = upload_array(h, mat.data(), mat.size() * sizeof(DevMat), &d)) != RT_OK) return rc;
+    tp.mat = (const DevMat*)d;
+
+    std::vector<rtd::DevTex> texs(std::max<uint64_t>(s->n_textures, 1));
+    for (uint64_t t = 0; t < s->n_textures; ++t) {
+        const rt_image& im = s->textures[t];
+        texs[t].rgb8 = nullptr; texs[t].width = im.width; texs[t].height = im.height;
+        if (im.rgb8 && im.width && im.height) {
+            if ((rc = upload_array(h, im.rgb8, im.width * im.height * 3, &d)) != RT_OK) return rc;
+            texs[t].rgb8 = (const uint8_t*)d;
+        }
+    }
+    if ((rc = upload_array(h, texs.data(), texs.size() * sizeof(rtd::DevTex), &d)) != RT_OK) return rc;
+    tp.tex = (const rtd::DevTex*)d;
+    tp.sky_mode = s->sky.mode;
+    tp.sky.rgb8 = nullptr; tp.sky.width = 0; tp.sky.height = 0;
+    if (s->sky.mode == RT_SKY_TEXTURE) {
+        if ((rc = upload_array(h, s->sky.tex.rgb8, s->sky.tex.width * s->sky.tex.height * 3, &d)) != RT_OK) return rc;
+        tp.sky.rgb8 = (const uint8_t*)d; tp.sky.width = s->sky.tex.width; tp.sky.height = s->sky.tex.height;
+    }
+
+    tp.n = n; tp.n_pairs = n_pairs; tp.n_lights = n_lights;
+    tp.gx = g[0]; tp.gy = g[1]; tp.gz = g[2];
+    tp.er_coef = 1.0f - (float)(96.0 * U);
+    tp.cam = s->camera;
+    tp.width = s->width; tp.height = s->height; tp.spp = s->samples_per_pixel; tp.max_depth = s->max_depth;
+    tp.key0 = (uint32_t)s->seed; tp.key1 = (uint32_t)(s->seed >> 32);
+    tp.rank = opts.rank; tp.world = opts.world; tp.band_rows = opts.band_rows;
+    tp.rows_local = rtb200_shard_rows(s->height, opts.rank, opts.world, opts.band_rows);
+    tp.npix_local = tp.rows_local * s->width;
+
+    // ---- launch geometry: persistent grid, 2 CTAs per SM; scene fully in shared memory when it fits ----
+    size_t per_cta_budget = ctx->max_smem;   // opt-in max per block (227 KB)
+    size_t half_budget = (228 * 1024 - 2 * 1024 * kCtasPerSm) / kCtasPerSm;   // two CTAs per SM incl. 1 KB/CTA reserve
+    size_t full_smem = trace_smem_bytes(n, n_pairs, true);
+    size_t filt_smem = trace_smem_bytes(n, n_pairs, false);
+    int ctas_per_sm = kCtasPerSm;
+    if (full_smem <= half_budget) { tp.scene_in_smem = 1; h->smem = full_smem; }
+    else if (filt_smem <= half_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; }
+    else if (full_smem <= per_cta_budget) { tp.scene_in_smem = 1; h->smem = full_smem; ctas_per_sm = 1; }
+    else if (filt_smem <= per_cta_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; ctas_per_sm = 1; }
+    else return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
+    h->grid = ctx->sm_count * ctas_per_sm;
+
+    // ---- per-sample staging: samples per batch bounded by the buffer cap ----
+    uint64_t cap = opts.sample_buffer_bytes ? opts.sample_buffer_bytes : (1ull << 30);
+    uint64_t per_spp = (uint64_t)std::max<uint32_t>(tp.npix_local, 1) * 16ull;
+    uint64_t spb = std::max<uint64_t>(1, cap / per_spp);
+    spb = std::min<uint64_t>(spb, s->samples_per_pixel);
+    while (spb > 1 && spb * tp.npix_local >= (1ull << 31)) spb /= 2;
+    h->spp_batch = (uint32_t)spb;
+
+    CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
+    guard.ok = true;
+    *out = h;
+    return RT_OK;
+}
+
+int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, rt_stats* stats) {
+    if (!h) return fail(RT_ERR_INVALID, "null scene handle");
+    auto wall0 = std::chrono::steady_clock::now();
+    DeviceCtx* ctx = h->ctx;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = stream_in ? (cudaStream_t)stream_in : ctx->stream;
+    TraceParams tp = h->tp;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (tp.npix_local == 0) return RT_OK;
+
+    const uint32_t spp = tp.spp, spb = h->spp_batch;
+    const uint32_t n_batches = (spp + spb - 1) / spb;
+    const uint32_t threads_total = (uint32_t)h->grid * kBlock;
+
+    CU(ctx->samplebuf.ensure((size_t)spb * tp.npix_local * 16));
+    CU(ctx->accum.ensure((size_t)tp.npix_local * 12));
+    CU(ctx->stack.ensure((size_t)std::max<uint32_t>(tp.max_depth, 1) * threads_total * 4));
+    CU(ctx->small.ensure(256 + (size_t)n_batches * 4));
+    while (ctx->ev.size() < 2 * (size_t)n_batches) {
+        cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
+    }
+    unsigned long long* stat = (unsigned long long*)ctx->small.p;
+    unsigned int* counters = (unsigned int*)((char*)ctx->small.p + 256);
+    CU(cudaMemsetAsync(ctx->small.p, 0, 256 + (size_t)n_batches * 4, st));
+
+    tp.samplebuf = (float4*)ctx->samplebuf.p;
+    tp.stack = (uint32_t*)ctx->stack.p;
+    tp.stack_stride = threads_total;
+    tp.stat = stat;
+
+    CU(cudaEventRecord(ctx->ev_begin, st));
+    uint32_t launches = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        tp.s0 = b * spb;
+        tp.s_count = std::min(spb, spp - tp.s0);
+        tp.total_work = tp.s_count * tp.npix_local;
+        tp.work_counter = counters + b;
+        CU(cudaEventRecord(ctx->ev[2 * b], st));
+        CU(launch_trace(tp, h->grid, h->smem, h->exact, st));
+        CU(cudaEventRecord(ctx->ev[2 * b + 1], st));
+        ResolveParams q{};
+        q.samplebuf = tp.samplebuf; q.accum = (float*)ctx->accum.p; q.npix_local = tp.npix_local; q.s_count = tp.s_count;
+        q.first = b == 0; q.last = b + 1 == n_batches; q.spp = spp;
+        q.out_linear = (float*)dev_linear_f32; q.out_rgb8 = (uint8_t*)dev_rgb8;
+        CU(launch_resolve(q, st));
+        launches += 2;
+    }
+    CU(cudaEventRecord(ctx->ev_end, st));
+    unsigned long long hstat[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(hstat, stat, sizeof hstat, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        stats->device_ms = ms;
+        double tr = 0.0;
+        for (uint32_t b = 0; b < n_batches; ++b) { CU(cudaEventElapsedTime(&ms, ctx->ev[2 * b], ctx->ev[2 * b + 1])); tr += ms; }
+        stats->trace_ms = tr;
+        stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3];
+        stats->kernel_launches = launches; stats->batches = n_batches;
+        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    }
+    return RT_OK;
+}
+
+static int render_host(const rt_scene* s, const rt_options* opts, uint8_t* out_rgb8, float* out_lin, rt_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    rtb200_scene_handle h = nullptr;
+    int rc = rtb200_scene_upload(s, opts, &h);
+    if (rc != RT_OK) return rc;
+    DeviceCtx* ctx = h->ctx;
+    size_t npl = h->tp.npix_local;
+    void *d8 = nullptr, *dl = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (out_rgb8) { e = ctx->out_rgb8.ensure(npl * 3 + 16); d8 = ctx->out_rgb8.p; }
+    if (e == cudaSuccess && out_lin) { e = ctx->out_lin.ensure(npl * 12 + 16); dl = ctx->out_lin.p; }
+    if (e != cudaSuccess) { rtb200_scene_release(h); return fail_cuda(e, "output buffer allocation"); }
+    rt_stats st{};
+    rc = rtb200_render_device(h, d8, dl, nullptr, &st);
+    if (rc == RT_OK && npl) {
+        if (out_rgb8) e = cudaMemcpyAsync(out_rgb8, d8, npl * 3, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && out_lin) e = cudaMemcpyAsync(out_lin, dl, npl * 12, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "device->host copy of the frame");
+    }
+    st.h2d_bytes = h->h2d_bytes;
+    st.d2h_bytes = (out_rgb8 ? npl * 3 : 0) + (out_lin ? npl * 12 : 0) + 32;
+    rtb200_scene_release(h);
+    st.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (stats) *stats = st;
+    return rc;
+}
+
+int rtb200_render_rgb8(const rt_scene* scene, const rt_options* opts, uint8_t* out_rgb8, rt_stats* stats) {
+    if (!scene || !out_rgb8) return fail(RT_ERR_INVALID, "null argument");
+    return render_host(scene, opts, out_rgb8, nullptr, stats);
+}
+int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, float* out_rgb, rt_stats* stats) {
+    if (!scene || !out_rgb) return fail(RT_ERR_INVALID, "null argument");
+    return render_host(scene, opts, nullptr, out_rgb, stats);
+}
+
+// ---- probes ------------------------------------------------------------------------------------------
+static int probe_io(const void* in, size_t in_bytes, size_t out_bytes, DeviceCtx** pctx, void** din, void** dout) {
+    int rc = get_ctx(-1, pctx);
+    if (rc != RT_OK) return rc;
+    DeviceCtx* c = *pctx;
+    CU(c->probe.ensure(in_bytes + out_bytes + 512));
+    *din = c->probe.p;
+    *dout = (char*)c->probe.p + ((in_bytes + 255) / 256) * 256;
+    CU(cudaMemsetAsync(*dout, 0, out_bytes, c->stream));
+    if (in_bytes) CU(cudaMemcpyAsync(*din, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    return RT_OK;
+}
+static int probe_finish(DeviceCtx* c, void* host_out, const void* dout, size_t out_bytes) {
+    CU(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rtb200_probe_sphere_hit(const rt_vec3* center, double radius, const rt_vec3* origin, const rt_vec3* dir, double t_min,
+                            double t_max, int32_t* hit, double* t, rt_vec3* point, rt_vec3* normal, int32_t* front_face) {
+    double in[12] = {center->x, center->y, center->z, radius, origin->x, origin->y, origin->z, dir->x, dir->y, dir->z, t_min, t_max};
+    double out[9];
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(in, sizeof in, sizeof out, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_sphere_hit((const double*)din, (double*)dout, c->stream));
+    if ((rc = probe_finish(c, out, dout, sizeof out)) != RT_OK) return rc;
+    *hit = out[0] != 0.0;
+    if (*hit) {
+        *t = out[1]; *point = rt_vec3{out[2], out[3], out[4]}; *normal = rt_vec3{out[5], out[6], out[7]};
+        *front_face = out[8] != 0.0;
+    }
+    return RT_OK;
+}
+int rtb200_probe_refract(const rt_vec3* uv, const rt_vec3* n, double eta, rt_vec3* o) {
+    double in[7] = {uv->x, uv->y, uv->z, n->x, n->y, n->z, eta}, out[3];
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(in, sizeof in, sizeof out, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_refract((const double*)din, (double*)dout, c->stream));
+    if ((rc = probe_finish(c, out, dout, sizeof out)) != RT_OK) return rc;
+    *o = rt_vec3{out[0], out[1], out[2]};
+    return RT_OK;
+}
+int rtb200_probe_reflectance(double cosine, double ref_idx, double* o) {
+    double in[2] = {cosine, ref_idx};
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(in, sizeof in, 8, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_reflectance((const double*)din, (double*)dout, c->stream));
+    return probe_finish(c, o, dout, 8);
+}
+int rtb200_probe_sky(const rt_vec3* dir, uint32_t sky_mode, float out_rgb[3]) {
+    if (sky_mode == RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "probe_sky supports none/gradient only");
+    double in[3] = {dir->x, dir->y, dir->z};
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(in, sizeof in, 12, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_sky((const double*)din, sky_mode, (float*)dout, c->stream));
+    return probe_finish(c, out_rgb, dout, 12);
+}
+int rtb200_probe_get_ray(const rt_camera* cam, double u, double v, rt_vec3* origin, rt_vec3* dir) {
+    struct { rt_camera cam; double uv[2]; } in;
+    in.cam = *cam; in.uv[0] = u; in.uv[1] = v;
+    double out[6];
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(&in, sizeof in, sizeof out, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_get_ray((const rt_camera*)din, (const double*)((char*)din + sizeof(rt_camera)), (double*)dout, c->stream));
+    if ((rc = probe_finish(c, out, dout, sizeof out)) != RT_OK) return rc;
+    *origin = rt_vec3{out[0], out[1], out[2]}; *dir = rt_vec3{out[3], out[4], out[5]};
+    return RT_OK;
+}
+int rtb200_probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t kind, uint32_t n, double* o) {
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(nullptr, 0, (size_t)n * 8, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_rng(seed, pixel, sample, kind, n, (double*)dout, c->stream));
+    return probe_finish(c, o, dout, (size_t)n * 8);
+}
+int rtb200_probe_quantise(const float* mean_linear, uint32_t n, uint8_t* o) {
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(mean_linear, (size_t)n * 4, n, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_quantise((const float*)din, n, (uint8_t*)dout, c->stream));
+    return probe_finish(c, o, dout, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// rtb200_kernels.cuh — parameter blocks and launch wrappers shared by rtb200_kernels.cu and rtb200_api.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtb200.h"
+#include "rtb200_device.cuh"
+
+namespace rtk {
+
+constexpr int kBlock = 256;        // threads per CTA of the trace kernel
+constexpr int kCtasPerSm = 2;
+constexpr int kMaxCand = 16;       // per-lane candidate slots in shared memory
+
+// 32-byte material record (device copy of the material half of rt_sphere)
+struct DevMat { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };
+static_assert(sizeof(DevMat) == 32, "DevMat must be 32 bytes");
+
+struct TraceParams {
+    // scene, resident in HBM
+    const float4*       filt;      // n_pairs*2 float4: {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}, recentred f32 filter records
+    const double4*      geo;       // n: {cx,cy,cz,radius} exact f64
+    const DevMat*       mat;       // n
+    const rtd::DevTex*  tex;       // n_tex
+    uint32_t n, n_pairs;
+    uint32_t n_lights;
+    uint32_t scene_in_smem;        // 1: geo+mat staged into shared memory as well
+    double gx, gy, gz;             // recentring offset of the filter frame
+    float  er_coef;                // per-ray error coefficient (see DESIGN.md "filter soundness")
+    rt_camera cam;
+    uint32_t width, height, spp, max_depth;
+    uint32_t sky_mode;
+    rtd::DevTex sky;
+    uint32_t key0, key1;           // Philox key = seed
+    // work of this launch: samples [s0, s0+s_count) of every pixel of the shard
+    uint32_t s0, s_count;
+    uint32_t npix_local, rows_local;
+    int32_t  rank, world;
+    uint32_t band_rows;
+    uint32_t total_work;           // npix_local * s_count
+    unsigned int* work_counter;
+    float4*  samplebuf;            // [s_count][npix_local] per-sample radiance (w = rays of the sample)
+    uint32_t* stack;               // [max_depth][stack_stride] per-lane albedo codes
+    uint32_t stack_stride;
+    unsigned long long* stat;      // [0]=rays [1]=candidates [2]=overflows [3]=samples
+};
+
+struct ResolveParams {
+    const float4* samplebuf;
+    float*   accum;        // [npix_local][3] running f32 sums in sample order
+    uint32_t npix_local, s_count;
+    uint32_t first, last;  // first batch zeroes accum, last batch writes outputs
+    uint32_t spp;
+    float*   out_linear;   // [npix_local][3] or null
+    uint8_t* out_rgb8;     // [npix_local][3] or null
+};
+
+size_t trace_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem);
+cudaError_t launch_trace(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st);
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t st);
+cudaError_t trace_configure(int device, int* sm_count, size_t* max_smem_optin);
+
+// single-thread probes of the device routines (known-answer tests)
+cudaError_t probe_sphere_hit(const double* in /*12*/, double* out /*9*/, cudaStream_t st);
+cudaError_t probe_refract(const double* in /*7*/, double* out /*3*/, cudaStream_t st);
+cudaError_t probe_reflectance(const double* in /*2*/, double* out /*1*/, cudaStream_t st);
+cudaError_t probe_sky(const double* in /*3*/, uint32_t mode, float* out /*3*/, cudaStream_t st);
+cudaError_t probe_get_ray(const rt_camera* cam_dev, const double* in /*2*/, double* out /*6*/, cudaStream_t st);
+cudaError_t probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t kind, uint32_t n, double* out, cudaStream_t st);
+cudaError_t probe_quantise(const float* in, uint32_t n, uint8_t* out, cudaStream_t st);
+
+}  // namespace rtk
