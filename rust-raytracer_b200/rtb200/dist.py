@@ -1,0 +1,97 @@
+"""Multi-GPU host path: one process per GPU (torchrun), image rows sharded over ranks, ONE framebuffer gather.
+
+The reference parallelises over independent row bands (raytracer.rs:254-262); here band b (band_rows rows) goes
+to rank b mod world. The per-(pixel,sample) counter RNG makes every pixel independent of the partition, so the
+gathered frame is bit-identical to the single-GPU frame. The only exchange step is the gather of the RGB8 (or
+linear f32) shards to rank 0 — torch.distributed.gather (NCCL send/recv over NVLink; gloo on CPU in the tests).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ResidentScene, Scene, make_options, shard_row_indices, shard_rows
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init(backend: Optional[str] = None):
+    rank, world, local = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def padded_rows(height: int, world: int, band_rows: int) -> int:
+    return max(shard_rows(height, r, world, band_rows) for r in range(world))
+
+
+def gather_frame(shard: torch.Tensor, height: int, world: int, band_rows: int, rank: int, out: Optional[torch.Tensor] = None,
+                 gather_buf: Optional[torch.Tensor] = None):
+    """Gather the ranks' compact row shards ([rows_r, W, C]) to rank 0 and de-interleave them into [H, W, C].
+    `shard` must already be padded to padded_rows() rows. Returns the frame on rank 0, None elsewhere."""
+    if world == 1:
+        return shard[:height]
+    rows_max = shard.shape[0]
+    if rank == 0:
+        if gather_buf is None:
+            gather_buf = torch.empty((world,) + tuple(shard.shape), dtype=shard.dtype, device=shard.device)
+        dist.gather(shard, list(gather_buf.unbind(0)), dst=0)
+        if out is None:
+            out = torch.empty((height,) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        if band_rows == 1:
+            # row y lives at gather_buf[y % world, y // world]
+            inter = gather_buf.transpose(0, 1).reshape((rows_max * world,) + tuple(shard.shape[1:]))
+            out.copy_(inter[:height])
+        else:
+            for r in range(world):
+                idx = torch.as_tensor(shard_row_indices(height, r, world, band_rows), device=shard.device)
+                out[idx] = gather_buf[r, : idx.numel()]
+        return out
+    dist.gather(shard, None, dst=0)
+    return None
+
+
+class DistributedRenderer:
+    """Scene resident on this rank's GPU; render() = trace the rank's rows, gather RGB8 to rank 0."""
+
+    def __init__(self, scene: Scene, band_rows: int = 1, variant: int = 0):
+        self.rank, self.world, self.local = env_rank_world()
+        self.scene = scene
+        self.band_rows = band_rows
+        self.h, self.w = scene.c.height, scene.c.width
+        self.device = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.device)
+        self.opts = make_options(device=self.local, rank=self.rank, world=self.world, band_rows=band_rows, variant=variant)
+        self.resident = ResidentScene(scene, self.opts)
+        self.rows = self.resident.rows
+        self.rows_max = padded_rows(self.h, self.world, band_rows)
+        self.shard = torch.zeros((self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device)
+        self.frame = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device) if self.rank == 0 else None
+        self.gbuf = torch.empty((self.world, self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) if (self.rank == 0 and self.world > 1) else None
+
+    def render(self) -> dict:
+        """One frame on the current torch stream. Returns this rank's stats; rank 0's `frame` holds the image."""
+        st = self.resident.render(self.shard.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        if self.world > 1:
+            gather_frame(self.shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
+        else:
+            self.frame = self.shard[: self.h]
+        return st
+
+    def release(self):
+        self.resident.release()
