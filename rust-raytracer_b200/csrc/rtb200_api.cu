@@ -231,8 +231,8 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
 
     // ---- device records ----
     const double U = 5.9604644775390625e-8;   // 2^-24
-    uint32_t n_pairs = (n + 1) / 2;
-    if (n_pairs == 0) n_pairs = 1;
+    uint32_t n_pairs = ((n + 1) / 2 + 3) / 4 * 4;   // the scan loop consumes blocks of 4 pairs; padding records never hit
+    if (n_pairs == 0) n_pairs = 4;
     std::vector<float> filt((size_t)n_pairs * 8);
     std::vector<double> geo((size_t)std::max<uint32_t>(n, 1) * 4, 0.0);
     std::vector<DevMat> mat(std::max<uint32_t>(n, 1));
@@ -250,7 +250,7 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
                 double nkd = -(c2 - r2) + Es;
                 cx = (float)x; cy = (float)y; cz = (float)z;
                 nk = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
-                if (!(std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz))) { cx = cy = cz = 0.f; nk = INFINITY; }
+                if (!(std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz)) || !(c2 < 1e30)) { cx = cy = cz = 0.f; nk = INFINITY; }   // always a candidate
                 geo[4 * (size_t)i + 0] = sp.center.x; geo[4 * (size_t)i + 1] = sp.center.y; geo[4 * (size_t)i + 2] = sp.center.z;
                 geo[4 * (size_t)i + 3] = sp.radius;
                 DevMat& m = mat[i];

@@ -175,9 +175,9 @@ RT_DEV uint32_t texture_texel(const DevTex& t, double h_offset, double u, double
 }
 
 // Miss branch of ray_color (raytracer.rs:134-163)
-RT_DEV void sky_color(D3 dir, uint32_t sky_mode, const DevTex& sky, float& r, float& g, float& b) {
+// `l` = dir.length() (the caller shares it with Glass lanes)
+RT_DEV void sky_color(D3 dir, double l, uint32_t sky_mode, const DevTex& sky, float& r, float& g, float& b) {
     if (sky_mode == RT_SKY_NONE) { r = 0.0f; g = 0.0f; b = 0.0f; return; }
-    double l = length(dir);
     float t = clampf(__fmul_rn(0.5f, __fadd_rn(__double2float_rn(__ddiv_rn(dir.y, l)), 1.0f)));
     if (sky_mode == RT_SKY_GRADIENT) {
         float omt = __fmul_rn(__fsub_rn(1.0f, t), 1.0f);

@@ -152,24 +152,34 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) rt_trace_kernel(const __gr
             const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
                          oz2 = make_float2(2.f * ofz, 2.f * ofz);
             const float2 nod2 = make_float2(nod, nod);
-            const uint32_t np = p.n_pairs;
-#pragma unroll 4
-            for (uint32_t pp = 0; pp < np; ++pp) {
-                float4 A = s_filt[2 * pp], B = s_filt[2 * pp + 1];
-                float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
-                float2 bb = __ffma2_rn(cz, dz2, nod2);
-                bb = __ffma2_rn(cy, dy2, bb);
-                bb = __ffma2_rn(cx, dx2, bb);
-                float2 tt = __ffma2_rn(cz, oz2, nk);
-                tt = __ffma2_rn(cy, oy2, tt);
-                tt = __ffma2_rn(cx, ox2, tt);
-                float2 D = __ffma2_rn(bb, bb, tt);
-                bool h0 = D.x >= thr, h1 = D.y >= thr;
-                if (h0 | h1) {
-                    if (h0) { if (nc < kMaxCand) s_cand[nc * kBlock + tid] = (uint16_t)(2 * pp); else ovf = true; ++nc; }
-                    if (h1) { if (nc < kMaxCand) s_cand[nc * kBlock + tid] = (uint16_t)(2 * pp + 1); else ovf = true; ++nc; }
+            // Blocks of 4 pairs (8 spheres): 8 LDS.128 + 28 FFMA2, branch-free; one rarely-taken branch per block
+            // appends the block's candidates (ascending index order is preserved).
+            const uint32_t np = p.n_pairs;   // host pads to a multiple of 4 with never-hit records
+#pragma unroll 2
+            for (uint32_t pp = 0; pp < np; pp += 4) {
+                float2 Dv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 A = s_filt[2 * (pp + q)], B = s_filt[2 * (pp + q) + 1];
+                    float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
+                    float2 bb = __ffma2_rn(cz, dz2, nod2);
+                    float2 tt = __ffma2_rn(cz, oz2, nk);
+                    bb = __ffma2_rn(cy, dy2, bb);
+                    tt = __ffma2_rn(cy, oy2, tt);
+                    bb = __ffma2_rn(cx, dx2, bb);
+                    tt = __ffma2_rn(cx, ox2, tt);
+                    Dv[q] = __ffma2_rn(bb, bb, tt);
+                }
+                float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
+                if (m >= thr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (Dv[q].x >= thr) { if (nc < kMaxCand) s_cand[nc * kBlock + tid] = (uint16_t)(2 * (pp + q)); ++nc; }
+                        if (Dv[q].y >= thr) { if (nc < kMaxCand) s_cand[nc * kBlock + tid] = (uint16_t)(2 * (pp + q) + 1); ++nc; }
+                    }
                 }
             }
+            if (nc > kMaxCand) ovf = true;
         } else {
             ovf = alive;
         }
@@ -191,55 +201,73 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) rt_trace_kernel(const __gr
         }
 
         // =========================== shade / scatter ===========================
+        // Staged so that lanes of different materials share the expensive pieces: one hit-record stage for all hit
+        // lanes, ONE rejection-sampling stage for Lambertian+Texture+Metal lanes, one vector-length stage for
+        // Glass+miss lanes.
         if (alive) {
             ++st_rays; ++rays_sample;
             float cr = 0.f, cg = 0.f, cb = 0.f;
             bool done = false;
-            if (best < 0) {
-                sky_color(d, p.sky_mode, p.sky, cr, cg, cb);
-                done = true;
-            } else {
+            const bool hit = best >= 0;
+            uint32_t kind = 0xffffffffu;
+            DevMat m; m.r = m.g = m.b = 0.f; m.kind = 0; m.param = 0.0; m.tex = -1; m.pad = 0;
+            HitRec h; h.point = o; h.normal = d; h.front_face = true;
+            D3 center = mk(0, 0, 0);
+            if (hit) {
                 double4 gq = geo[best];
-                D3 center = mk(gq.x, gq.y, gq.z);
-                HitRec h = hit_record(center, gq.w, o, d, best_t);
-                const DevMat m = mat[best];
-                uint32_t code = (uint32_t)best;
-                D3 nd = d;
-                bool scattered = true;
-                if (m.kind == RT_LAMBERTIAN || m.kind == RT_TEXTURE) {          // materials.rs:84-95, 256-267
-                    D3 sd = add(h.normal, random_in_unit_sphere(rng, k0, k1));
+                center = mk(gq.x, gq.y, gq.z);
+                h = hit_record(center, gq.w, o, d, best_t);
+                m = mat[best];
+                kind = m.kind;
+            }
+            const bool is_diffuse = kind == RT_LAMBERTIAN || kind == RT_TEXTURE;
+            const bool is_metal = kind == RT_METAL, is_glass = kind == RT_GLASS;
+            uint32_t code = (uint32_t)best;
+            D3 nd = d;
+            bool scattered = hit;
+            if (is_diffuse || is_metal) {
+                D3 rs = random_in_unit_sphere(rng, k0, k1);
+                if (is_diffuse) {                                               // materials.rs:84-95, 256-267
+                    D3 sd = add(h.normal, rs);
                     if (near_zero(sd)) sd = h.normal;
                     D3 target = add(h.point, sd);
                     nd = sub(target, h.point);
-                    if (m.kind == RT_TEXTURE) {
-                        double tu, tv;
-                        sphere_uv(sub(h.point, center), tu, tv);
-                        code = 0x80000000u | texture_texel(p.tex[m.tex], m.param, tu, tv);
-                    }
-                } else if (m.kind == RT_METAL) {                                 // materials.rs:115-129
+                } else {                                                        // materials.rs:115-129
                     D3 refl = reflect(d, h.normal);
-                    nd = add(refl, mul(random_in_unit_sphere(rng, k0, k1), m.param));
+                    nd = add(refl, mul(rs, m.param));
                     if (!(dot(nd, h.normal) > 0.0)) { scattered = false; done = true; }   // absorbed -> black
-                } else if (m.kind == RT_GLASS) {                                 // materials.rs:176-199
+                }
+            }
+            if (kind == RT_TEXTURE) {
+                double tu, tv;
+                sphere_uv(sub(h.point, center), tu, tv);
+                code = 0x80000000u | texture_texel(p.tex[m.tex], m.param, tu, tv);
+            }
+            if (is_glass || !hit) {
+                const double len = length(d);                                   // unit_vector: point3d.rs:63-70
+                if (is_glass) {                                                 // materials.rs:176-199
                     double ratio = h.front_face ? __ddiv_rn(1.0, m.param) : m.param;
-                    D3 ud = unit_vector(d);
+                    D3 ud = divs(d, len);
                     double cos_theta = fmin(dot(neg(ud), h.normal), 1.0);
                     double sin_theta = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cos_theta, cos_theta)));
-                    bool cannot_refract = __dmul_rn(ratio, sin_theta) > 1.0;
-                    bool refl = cannot_refract;
-                    if (!refl) refl = reflectance(cos_theta, ratio) > rng_f64(rng, k0, k1);
+                    bool refl = __dmul_rn(ratio, sin_theta) > 1.0;              // cannot_refract
+                    if (!refl) refl = reflectance(cos_theta, ratio) > rng_f64(rng, k0, k1);   // drawn only if refraction is possible
                     nd = refl ? reflect(ud, h.normal) : refract(ud, h.normal, ratio);
-                } else {                                                         // Light, materials.rs:65-69
-                    cr = 1.f; cg = 1.f; cb = 1.f;
-                    scattered = false; done = true;
+                } else {                                                        // miss: raytracer.rs:134-163
+                    sky_color(d, len, p.sky_mode, p.sky, cr, cg, cb);
+                    done = true;
                 }
-                if (scattered) {
-                    p.stack[(size_t)level * p.stack_stride + gtid] = code;
-                    ++level;
-                    --depth_left;
-                    o = h.point; d = nd;
-                    if (depth_left == 0) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
-                }
+            }
+            if (kind == RT_LIGHT) {                                             // materials.rs:65-69
+                cr = 1.f; cg = 1.f; cb = 1.f;
+                scattered = false; done = true;
+            }
+            if (scattered) {
+                p.stack[(size_t)level * p.stack_stride + gtid] = code;
+                ++level;
+                --depth_left;
+                o = h.point; d = nd;
+                if (depth_left == 0) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
             }
             if (done) {
                 // unwind the recursion: c = clamp(light + albedo * c) per level, innermost first (raytracer.rs:117-122)
@@ -350,7 +378,8 @@ __global__ void k_probe_refract(const double* in, double* out) {
 __global__ void k_probe_reflectance(const double* in, double* out) { out[0] = reflectance(in[0], in[1]); }
 __global__ void k_probe_sky(const double* in, uint32_t mode, float* out) {
     DevTex none; none.rgb8 = nullptr; none.width = 0; none.height = 0;
-    sky_color(mk(in[0], in[1], in[2]), mode, none, out[0], out[1], out[2]);
+    D3 dd = mk(in[0], in[1], in[2]);
+    sky_color(dd, length(dd), mode, none, out[0], out[1], out[2]);
 }
 __global__ void k_probe_get_ray(const rt_camera* cam, const double* in, double* out) {
     D3 o, d;

@@ -1,0 +1,21 @@
+#!/usr/bin/env python3
+"""Render a BASELINE config resident N times (profiling target). usage: render_once.py [C2] [reps] [variant]"""
+import sys, os
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, 'rust-raytracer_b200'))
+import rtb200 as R
+from rtb200 import scenes
+import torch
+name = sys.argv[1] if len(sys.argv) > 1 else 'C2'
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if 'x' in name:
+    w, h, spp = (int(v) for v in name.split('x'))
+    sc = scenes.cover_scene(w, h, spp)
+else:
+    sc = scenes.scene(name)
+rs = R.ResidentScene(sc, R.make_options(variant=variant))
+out = torch.empty(sc.c.height * sc.c.width * 3, dtype=torch.uint8, device='cuda')
+for i in range(reps):
+    st = rs.render(out.data_ptr())
+    print(f"{name}: rays={st['rays']} device_ms={st['device_ms']:.3f} trace_ms={st['trace_ms']:.3f} Mrays/s={st['rays']/st['device_ms']/1e3:.1f} cand/ray={st['candidates']/max(st['rays'],1):.2f}", flush=True)
