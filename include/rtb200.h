@@ -85,8 +85,9 @@ typedef struct {
 
 enum rt_trace_variant {
     RT_VARIANT_AUTO      = 0,
-    RT_VARIANT_FILTERED  = 1, /* f32 conservative filter + exact f64 confirmation (default)   */
-    RT_VARIANT_EXACT_F64 = 2  /* every sphere tested in f64 (validation of the filter)        */
+    RT_VARIANT_FILTERED  = 1, /* CTA-wavefront kernel: f32 conservative filter + exact f64 confirmation (default) */
+    RT_VARIANT_EXACT_F64 = 2, /* every sphere tested in f64 (validation of the filter)        */
+    RT_VARIANT_LANES     = 3  /* lane-autonomous persistent kernel (no CTA-level sorting); kept for comparison */
 };
 
 /* Which rows this call renders. Row-band b (band_rows consecutive rows) belongs to shard

@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -112,6 +113,8 @@ struct rtb200_scene_t {
     TraceParams tp{};
     rt_options opts{};
     bool exact = false;
+    bool lanes = false;
+    int block = 256;
     int grid = 0;
     size_t smem = 0;
     uint32_t spp_batch = 0;
@@ -215,6 +218,8 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     rtb200_scene_t* h = new rtb200_scene_t();
     h->device = ctx->device; h->ctx = ctx; h->opts = opts;
     h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
+    h->lanes = (opts.variant == RT_VARIANT_LANES);
+    if (opts.variant > RT_VARIANT_LANES) return fail(RT_ERR_INVALID, "unknown variant");
     struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
 
     // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
@@ -231,8 +236,8 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
 
     // ---- device records ----
     const double U = 5.9604644775390625e-8;   // 2^-24
-    uint32_t n_pairs = ((n + 1) / 2 + 3) / 4 * 4;   // the scan loop consumes blocks of 4 pairs; padding records never hit
-    if (n_pairs == 0) n_pairs = 4;
+    uint32_t n_pairs = ((n + 1) / 2 + 7) / 8 * 8;   // the scan loop consumes 2 blocks of 4 pairs per trip; padding records never hit
+    if (n_pairs == 0) n_pairs = 8;
     std::vector<float> filt((size_t)n_pairs * 8);
     std::vector<double> geo((size_t)std::max<uint32_t>(n, 1) * 4, 0.0);
     std::vector<DevMat> mat(std::max<uint32_t>(n, 1));
@@ -301,18 +306,38 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     tp.rows_local = rtb200_shard_rows(s->height, opts.rank, opts.world, opts.band_rows);
     tp.npix_local = tp.rows_local * s->width;
 
-    // ---- launch geometry: persistent grid, 2 CTAs per SM; scene fully in shared memory when it fits ----
-    size_t per_cta_budget = ctx->max_smem;   // opt-in max per block (227 KB)
-    size_t half_budget = (228 * 1024 - 2 * 1024 * kCtasPerSm) / kCtasPerSm;   // two CTAs per SM incl. 1 KB/CTA reserve
-    size_t full_smem = trace_smem_bytes(n, n_pairs, true);
-    size_t filt_smem = trace_smem_bytes(n, n_pairs, false);
-    int ctas_per_sm = kCtasPerSm;
-    if (full_smem <= half_budget) { tp.scene_in_smem = 1; h->smem = full_smem; }
-    else if (filt_smem <= half_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; }
-    else if (full_smem <= per_cta_budget) { tp.scene_in_smem = 1; h->smem = full_smem; ctas_per_sm = 1; }
-    else if (filt_smem <= per_cta_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; ctas_per_sm = 1; }
-    else return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
-    h->grid = ctx->sm_count * ctas_per_sm;
+    // ---- launch geometry: persistent grid = SMs x resident CTAs; scene fully in shared memory when it fits ----
+    if (h->lanes) {
+        size_t per_cta_budget = ctx->max_smem;   // opt-in max per block (227 KB)
+        size_t half_budget = (228 * 1024 - 2 * 1024 * kCtasPerSm) / kCtasPerSm;
+        size_t full_smem = trace_smem_bytes(n, n_pairs, true);
+        size_t filt_smem = trace_smem_bytes(n, n_pairs, false);
+        int ctas_per_sm = kCtasPerSm;
+        if (full_smem <= half_budget) { tp.scene_in_smem = 1; h->smem = full_smem; }
+        else if (filt_smem <= half_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; }
+        else if (full_smem <= per_cta_budget) { tp.scene_in_smem = 1; h->smem = full_smem; ctas_per_sm = 1; }
+        else if (filt_smem <= per_cta_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; ctas_per_sm = 1; }
+        else return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
+        h->grid = ctx->sm_count * ctas_per_sm;
+    } else {
+        // Candidate configurations: CTA size x {geometry+materials in shared memory or read through L1}. Pick the one
+        // with the most resident threads per SM; ties go to the larger CTA (better class sorting), then to smem scene.
+        // RTB200_WF_BLOCK / RTB200_WF_SCENE_SMEM override the choice (tuning experiments).
+        const char* eb = getenv("RTB200_WF_BLOCK"); const char* es = getenv("RTB200_WF_SCENE_SMEM");
+        int best_threads = -1;
+        for (int blk : {256, 128}) {
+            if (eb && atoi(eb) != blk) continue;
+            for (int in_smem : {1, 0}) {
+                if (es && atoi(es) != in_smem) continue;
+                size_t sm = wavefront_smem_bytes(n, n_pairs, in_smem != 0, blk);
+                if (sm > ctx->max_smem) continue;
+                int occ = wavefront_max_ctas_per_sm(sm, blk);
+                if (occ * blk > best_threads) { best_threads = occ * blk; h->block = blk; h->smem = sm; tp.scene_in_smem = (uint32_t)in_smem; h->grid = ctx->sm_count * occ; }
+            }
+        }
+        if (best_threads <= 0)
+            return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
+    }
 
     // ---- per-sample staging: samples per batch bounded by the buffer cap ----
     uint64_t cap = opts.sample_buffer_bytes ? opts.sample_buffer_bytes : (1ull << 30);
@@ -340,7 +365,7 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
 
     const uint32_t spp = tp.spp, spb = h->spp_batch;
     const uint32_t n_batches = (spp + spb - 1) / spb;
-    const uint32_t threads_total = (uint32_t)h->grid * kBlock;
+    const uint32_t threads_total = (uint32_t)h->grid * (uint32_t)(h->lanes ? kBlock : h->block);
 
     CU(ctx->samplebuf.ensure((size_t)spb * tp.npix_local * 16));
     CU(ctx->accum.ensure((size_t)tp.npix_local * 12));
@@ -366,7 +391,13 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         tp.total_work = tp.s_count * tp.npix_local;
         tp.work_counter = counters + b;
         CU(cudaEventRecord(ctx->ev[2 * b], st));
-        CU(launch_trace(tp, h->grid, h->smem, h->exact, st));
+        if (tp.max_depth == 0) {
+            CU(cudaMemsetAsync(tp.samplebuf, 0, (size_t)tp.total_work * 16, st));   // ray_color(depth 0) = black, no ray (raytracer.rs:80-82)
+        } else if (h->lanes) {
+            CU(launch_trace(tp, h->grid, h->smem, false, st));
+        } else {
+            CU(launch_wavefront(tp, h->grid, h->smem, h->block, h->exact, st));
+        }
         CU(cudaEventRecord(ctx->ev[2 * b + 1], st));
         ResolveParams q{};
         q.samplebuf = tp.samplebuf; q.accum = (float*)ctx->accum.p; q.npix_local = tp.npix_local; q.s_count = tp.s_count;
@@ -376,7 +407,7 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         launches += 2;
     }
     CU(cudaEventRecord(ctx->ev_end, st));
-    unsigned long long hstat[4] = {0, 0, 0, 0};
+    unsigned long long hstat[16] = {0};
     CU(cudaMemcpyAsync(hstat, stat, sizeof hstat, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (stats) {
@@ -387,6 +418,11 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         for (uint32_t b = 0; b < n_batches; ++b) { CU(cudaEventElapsedTime(&ms, ctx->ev[2 * b], ctx->ev[2 * b + 1])); tr += ms; }
         stats->trace_ms = tr;
         stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3];
+        if (getenv("RTB200_PRINT_PHASES")) {
+            fprintf(stderr, "[rtb200] ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
+                    hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
+        }
+        if (tp.max_depth == 0) stats->samples = (uint64_t)tp.npix_local * spp;   // no kernel ran: every sample is black
         stats->kernel_launches = launches; stats->batches = n_batches;
         stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     }

@@ -9,8 +9,12 @@
 namespace rtk {
 
 constexpr int kBlock = 256;        // threads per CTA of the trace kernel
-constexpr int kCtasPerSm = 2;
-constexpr int kMaxCand = 16;       // per-lane candidate slots in shared memory
+constexpr int kCtasPerSm = 2;        // lane-autonomous kernel (rt_trace_kernel)
+#ifndef RT_WF_THREADS
+#define RT_WF_THREADS 768
+#endif
+constexpr int kWfThreadsPerSm = RT_WF_THREADS;  // CTA-wavefront kernel (rt_wavefront_kernel): resident threads per SM the register budget targets
+constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory
 
 // 32-byte material record (device copy of the material half of rt_sphere)
 struct DevMat { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };
@@ -57,6 +61,9 @@ struct ResolveParams {
 
 size_t trace_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem);
 cudaError_t launch_trace(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st);
+size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem, int block);
+cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st);
+int wavefront_max_ctas_per_sm(size_t smem, int block);
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t st);
 cudaError_t trace_configure(int device, int* sm_count, size_t* max_smem_optin);
 

@@ -1,0 +1,433 @@
+// rtb200_wavefront.cu — the production trace kernel: a persistent-threads WAVEFRONT tracer at CTA scope.
+//
+// One persistent CTA (256 threads) per resident slot of every SM owns a pool of 256 ray slots in shared memory,
+// laid out SoA, next to the scene's sphere/material records (staged once by 1-D TMA bulk copies). Until the global
+// (pixel,sample) queue is drained and the pool is empty, the CTA repeats three barrier-separated stages:
+//
+//   closest-hit   thread t <-> slot t. hit_world (raytracer.rs:44-59) over ALL spheres as a conservative f32 filter
+//                 (7 FMA per sphere, two spheres per packed FFMA2, blocks of 8 spheres without a branch) that appends
+//                 candidates to a per-thread list, then the reference-exact f64 Sphere::hit (sphere.rs:46-78) on the
+//                 candidates only (ascending index: ties go to the first sphere like raytracer.rs:52-56).
+//   sort          rays are classified {miss, diffuse, metal, glass, light} and compacted class by class with warp
+//                 ballots + one shared-memory atomic per (warp, class): perm[] lists the live slots sorted by class.
+//   shade+ray-gen thread i <-> slot perm[i], so a warp shades ONE material: Material::scatter (materials.rs:44-54) or
+//                 the sky (raytracer.rs:134-163), iteratively (no recursion): albedo codes go to a per-slot stack that
+//                 is unwound backwards on termination so the f32 products associate exactly like the reference's
+//                 recursion (raytracer.rs:117-122). A terminated path writes its sample and the same thread
+//                 immediately regenerates the slot from the queue (render_line's jitter + Camera::get_ray,
+//                 raytracer.rs:199-201): one warp-aggregated atomic pops the work items.
+//
+// FMA-pipe work (closest-hit) of one CTA overlaps FP64-pipe work (shade) of the other CTAs resident on the SM.
+#include "rtb200_kernels.cuh"
+
+using namespace rtd;
+
+namespace rtk {
+
+namespace {
+
+enum : uint32_t { CLS_MISS = 0, CLS_DIFFUSE = 1, CLS_METAL = 2, CLS_GLASS = 3, CLS_LIGHT = 4, CLS_DEAD = 5, N_CLS = 6 };
+constexpr uint32_t kDeadLevel = 0xffffffffu;
+
+struct WfSmem {
+    uint32_t filt_off, geo_off, mat_off, cand_off;
+    uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each
+    uint32_t bi, work, pix, smp, blk, clo, chi, lvl;   // uint32[kBlock] each
+    uint32_t perm;                                  // uint16[kBlock]
+    uint32_t cnt;                                   // uint32[2][8]
+    uint32_t flags;                                 // uint32[4]
+    uint32_t total;
+};
+
+__host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, bool scene_in_smem, uint32_t kBlock) {
+    WfSmem L;
+    uint32_t off = 16;   // mbarrier
+    L.filt_off = off; off += n_pairs * 32u;
+    L.geo_off = off; if (scene_in_smem) off += n * 32u;
+    L.mat_off = off; if (scene_in_smem) off += n * 32u;
+    L.cand_off = off; off += (uint32_t)kMaxCand * kBlock * 2u;
+    L.ox = off; off += kBlock * 8u; L.oy = off; off += kBlock * 8u; L.oz = off; off += kBlock * 8u;
+    L.dx = off; off += kBlock * 8u; L.dy = off; off += kBlock * 8u; L.dz = off; off += kBlock * 8u;
+    L.bt = off; off += kBlock * 8u;
+    L.bi = off; off += kBlock * 4u; L.work = off; off += kBlock * 4u; L.pix = off; off += kBlock * 4u; L.smp = off; off += kBlock * 4u;
+    L.blk = off; off += kBlock * 4u; L.clo = off; off += kBlock * 4u; L.chi = off; off += kBlock * 4u; L.lvl = off; off += kBlock * 4u;
+    L.perm = off; off += kBlock * 2u;
+    L.cnt = off; off += 2u * 8u * 4u;
+    L.flags = off; off += 16u;
+    L.total = off;
+    return L;
+}
+
+RT_DEV void bulk_stage(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t CH = 32768u;
+    for (uint32_t o = 0; o < bytes; o += CH) {
+        uint32_t nb = bytes - o < CH ? bytes - o : CH;
+        tma_bulk_g2s((char*)dst + o, (const char*)src + o, nb, bar);
+    }
+}
+
+RT_DEV void albedo_of(uint32_t code, const DevMat* mat, float& r, float& g, float& b) {
+    if (code & 0x80000000u) {   // packed texel (materials.rs:248-252: pixel as f32 / 255.0)
+        r = __fdiv_rn((float)(code & 0xffu), 255.0f);
+        g = __fdiv_rn((float)((code >> 8) & 0xffu), 255.0f);
+        b = __fdiv_rn((float)((code >> 16) & 0xffu), 255.0f);
+    } else {
+        const DevMat& m = mat[code];
+        r = m.r; g = m.g; b = m.b;
+    }
+}
+
+}  // namespace
+
+size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem, int block) { return wf_layout(n, n_pairs, scene_in_smem, (uint32_t)block).total; }
+
+template <int kBlock, bool EXACT>
+__global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const WfSmem L = wf_layout(p.n, p.n_pairs, p.scene_in_smem != 0, kBlock);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    const float4* s_filt = reinterpret_cast<const float4*>(smem_raw + L.filt_off);
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem_raw + L.cand_off);
+    const double4* geo = p.scene_in_smem ? reinterpret_cast<const double4*>(smem_raw + L.geo_off) : p.geo;
+    const DevMat* mat = p.scene_in_smem ? reinterpret_cast<const DevMat*>(smem_raw + L.mat_off) : p.mat;
+    double* s_ox = reinterpret_cast<double*>(smem_raw + L.ox); double* s_oy = reinterpret_cast<double*>(smem_raw + L.oy);
+    double* s_oz = reinterpret_cast<double*>(smem_raw + L.oz); double* s_dx = reinterpret_cast<double*>(smem_raw + L.dx);
+    double* s_dy = reinterpret_cast<double*>(smem_raw + L.dy); double* s_dz = reinterpret_cast<double*>(smem_raw + L.dz);
+    double* s_bt = reinterpret_cast<double*>(smem_raw + L.bt);
+    uint32_t* s_bi = reinterpret_cast<uint32_t*>(smem_raw + L.bi); uint32_t* s_work = reinterpret_cast<uint32_t*>(smem_raw + L.work);
+    uint32_t* s_pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix); uint32_t* s_smp = reinterpret_cast<uint32_t*>(smem_raw + L.smp);
+    uint32_t* s_blk = reinterpret_cast<uint32_t*>(smem_raw + L.blk); uint32_t* s_clo = reinterpret_cast<uint32_t*>(smem_raw + L.clo);
+    uint32_t* s_chi = reinterpret_cast<uint32_t*>(smem_raw + L.chi); uint32_t* s_lvl = reinterpret_cast<uint32_t*>(smem_raw + L.lvl);
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + L.perm);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + L.cnt);
+    volatile uint32_t* s_flags = reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags);   // [0] = queue exhausted
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t k0 = p.key0, k1 = p.key1;
+    const uint32_t stack_col = blockIdx.x * kBlock;   // this CTA's columns of the albedo stack
+
+    // ---- stage the scene into shared memory (TMA bulk copies, one mbarrier) ----
+    if (tid == 0) mbar_init(bar, 1);
+    if (tid < 16) s_cnt[tid] = 0;
+    if (tid < 4) s_flags[tid] = 0;
+    s_lvl[tid] = kDeadLevel;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = p.n_pairs * 32u + (p.scene_in_smem ? p.n * 64u : 0u);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_stage(smem_raw + L.filt_off, p.filt, p.n_pairs * 32u, bar);
+        if (p.scene_in_smem) {
+            bulk_stage(smem_raw + L.geo_off, p.geo, p.n * 32u, bar);
+            bulk_stage(smem_raw + L.mat_off, p.mat, p.n * 32u, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0;
+#ifdef RT_PROFILE_PHASES
+    unsigned long long pf_scan = 0, pf_confirm = 0, pf_waitA = 0, pf_sort = 0, pf_shade = 0, pf_waitC = 0, pf_iters = 0, pf_t = clock64();
+#define PF_MARK(acc) { unsigned long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; }
+#else
+#define PF_MARK(acc)
+#endif
+
+    // Regenerate slot `s` from the global (pixel,sample) queue. Warp-synchronous: every lane of the warp calls it,
+    // `want` says whether this lane's slot needs a new path. raytracer.rs:199-201 + camera.rs:79-84.
+    auto regenerate = [&](bool want, uint32_t s) {
+        want = want && (s_flags[0] == 0u);
+        unsigned need = __ballot_sync(FULL, want);
+        if (!need) return;
+        int leader = __ffs(need) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(p.work_counter, (unsigned)__popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!want) return;
+        unsigned my = base + __popc(need & ((1u << lane) - 1u));
+        if (my >= p.total_work) { s_flags[0] = 1u; return; }
+        uint32_t s_local = my / p.npix_local;
+        uint32_t lp = my - s_local * p.npix_local;
+        uint32_t y_local = lp / p.width, x = lp - y_local * p.width;
+        uint32_t band = y_local / p.band_rows;
+        uint32_t y = (band * (uint32_t)p.world + (uint32_t)p.rank) * p.band_rows + (y_local - band * p.band_rows);
+        Rng rng; rng_init(rng, y * p.width + x, p.s0 + s_local);
+        double xi1 = rng_f64(rng, k0, k1);
+        double u = __ddiv_rn(__dadd_rn((double)x, xi1), __dsub_rn((double)p.width, 1.0));
+        double xi2 = rng_f64(rng, k0, k1);
+        double v = __ddiv_rn(__dsub_rn((double)p.height, __dadd_rn((double)y, xi2)), __dsub_rn((double)p.height, 1.0));
+        D3 o, d;
+        get_ray(p.cam, u, v, o, d);
+        s_ox[s] = o.x; s_oy[s] = o.y; s_oz[s] = o.z; s_dx[s] = d.x; s_dy[s] = d.y; s_dz[s] = d.z;
+        s_work[s] = my; s_pix[s] = rng.pixel; s_smp[s] = rng.sample;
+        s_blk[s] = (rng.blk << 1) | rng.has; s_clo[s] = rng.c_lo; s_chi[s] = rng.c_hi;
+        s_lvl[s] = 0u;
+        ++st_samples;
+    };
+
+    regenerate(true, (uint32_t)tid);   // initial fill of the pool
+    __syncthreads();
+
+    uint32_t it = 0;
+    for (;; ++it) {
+        uint32_t* cnt = s_cnt + (it & 1u) * 8u;
+        // =========================== closest-hit: thread t <-> slot t ===========================
+        const bool alive = s_lvl[tid] != kDeadLevel;
+        uint32_t cls = CLS_DEAD;
+        {
+            const D3 o = mk(s_ox[tid], s_oy[tid], s_oz[tid]), d = mk(s_dx[tid], s_dy[tid], s_dz[tid]);
+            int nc = 0;
+            bool ovf = false;
+            const double a = length_squared(d);
+            if (!EXACT) {
+                // per-ray filter constants in the recentred f32 frame (DESIGN.md "filter soundness")
+                float ofx = __double2float_rn(__dsub_rn(o.x, p.gx)), ofy = __double2float_rn(__dsub_rn(o.y, p.gy)),
+                      ofz = __double2float_rn(__dsub_rn(o.z, p.gz));
+                float dfx = __double2float_rn(d.x), dfy = __double2float_rn(d.y), dfz = __double2float_rn(d.z);
+                float s = fmaf(dfx, dfx, fmaf(dfy, dfy, dfz * dfz));
+                float oo = fmaf(ofx, ofx, fmaf(ofy, ofy, ofz * ofz));
+                bool ok = (s > 1e-30f) && (s < 1e30f) && (oo < 1e30f);
+                float inv = rsqrtf(s);
+                float dnx = dfx * inv, dny = dfy * inv, dnz = dfz * inv;
+                float nod = -fmaf(ofx, dnx, fmaf(ofy, dny, ofz * dnz));
+                float thr = __fmul_rd(oo, p.er_coef);
+                if (!alive) thr = __int_as_float(0x7f800000);   // +inf: empty slots never produce candidates
+                if (alive && !ok) { ovf = true; thr = __int_as_float(0x7f800000); }
+                const float2 dx2 = make_float2(dnx, dnx), dy2 = make_float2(dny, dny), dz2 = make_float2(dnz, dnz);
+                const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
+                             oz2 = make_float2(2.f * ofz, 2.f * ofz);
+                const float2 nod2 = make_float2(nod, nod);
+                const uint32_t np = p.n_pairs;   // multiple of 4; padding records never hit
+                // candidate column of this thread as a 32-bit shared-memory address; appends are predicated (no branch)
+                const uint32_t c_base = smem_u32(s_cand + tid);
+                const uint32_t c_full = c_base + (uint32_t)(kMaxCand - 8) * kBlock * 2u;
+                uint32_t c_addr = c_base;
+#pragma unroll 2
+                for (uint32_t pp = 0; pp < np; pp += 4) {
+                    float2 Dv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 A = s_filt[2 * (pp + q)], B = s_filt[2 * (pp + q) + 1];
+                        float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
+                        float2 bb = __ffma2_rn(cz, dz2, nod2);
+                        float2 tt = __ffma2_rn(cz, oz2, nk);
+                        bb = __ffma2_rn(cy, dy2, bb);
+                        tt = __ffma2_rn(cy, oy2, tt);
+                        bb = __ffma2_rn(cx, dx2, bb);
+                        tt = __ffma2_rn(cx, ox2, tt);
+                        Dv[q] = __ffma2_rn(bb, bb, tt);
+                    }
+                    float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
+                    if (m >= thr) {   // rare: some lane has a candidate among these 8 spheres; appends in ascending index order
+                        if (c_addr > c_full) { ovf = true; }
+                        else {
+                            const uint32_t j0 = 2u * pp;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}"
+                                             : "+r"(c_addr) : "f"(Dv[q].x), "f"(thr), "r"(j0 + 2u * q), "n"(kBlock * 2) : "memory");
+                                asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}"
+                                             : "+r"(c_addr) : "f"(Dv[q].y), "f"(thr), "r"(j0 + 2u * q + 1u), "n"(kBlock * 2) : "memory");
+                            }
+                        }
+                    }
+                }
+                nc = (int)((c_addr - c_base) / (kBlock * 2u));
+            } else {
+                ovf = alive;
+            }
+            PF_MARK(pf_scan)
+            // exact f64 confirmation, ascending sphere index => first index wins ties like raytracer.rs:52-56
+            if (alive) {
+                double best_t = DBL_MAX;
+                int best = -1;
+                const int cnt_c = ovf ? (int)p.n : nc;
+                if (ovf) ++st_ovf;
+                st_cand += (unsigned)cnt_c;
+                for (int k = 0; k < cnt_c; ++k) {
+                    int j = ovf ? k : (int)s_cand[k * kBlock + tid];
+                    if (j >= (int)p.n) continue;   // padding record
+                    double4 gq = geo[j];
+                    double root;
+                    if (sphere_root(mk(gq.x, gq.y, gq.z), gq.w, o, d, a, 0.001, best_t, root)) { best_t = root; best = j; }
+                }
+                s_bt[tid] = best_t;
+                s_bi[tid] = (uint32_t)best;
+                cls = CLS_MISS;
+                if (best >= 0) {
+                    uint32_t kind = mat[best].kind;
+                    cls = (kind == RT_METAL) ? CLS_METAL : (kind == RT_GLASS) ? CLS_GLASS : (kind == RT_LIGHT) ? CLS_LIGHT : CLS_DIFFUSE;
+                }
+                ++st_rays;
+            }
+        }
+
+        PF_MARK(pf_confirm)
+        // =========================== sort: compact the live slots class by class ===========================
+        uint32_t wbase = 0, rank = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < CLS_DEAD; ++c) {
+            unsigned b = __ballot_sync(FULL, cls == c);
+            if (b) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(b));
+                base = __shfl_sync(FULL, base, 0);
+                if (cls == c) { wbase = base; rank = __popc(b & ((1u << lane) - 1u)); }
+            }
+        }
+        PF_MARK(pf_sort)
+        __syncthreads();   // A: class counts complete
+        PF_MARK(pf_waitA)
+        uint32_t c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3], c4 = cnt[4];
+        const uint32_t e0 = c0, e1 = e0 + c1, e2 = e1 + c2, e3 = e2 + c3, n_live = e3 + c4;   // class end offsets
+        if (cls != CLS_DEAD) {
+            uint32_t start = cls == 0 ? 0u : cls == 1 ? e0 : cls == 2 ? e1 : cls == 3 ? e2 : e3;
+            s_perm[start + wbase + rank] = (uint16_t)tid;
+        }
+        if (tid < 8) s_cnt[((it + 1u) & 1u) * 8u + tid] = 0u;   // reset the other counter set for the next iteration
+        __syncthreads();   // B: perm complete
+        PF_MARK(pf_sort)
+
+        // =========================== shade + regenerate: thread i <-> slot perm[i] ===========================
+        bool still_alive = false;
+        {
+            const bool active = (uint32_t)tid < n_live;
+            const uint32_t s = active ? (uint32_t)s_perm[tid] : 0u;
+            const uint32_t c = !active ? CLS_DEAD : ((uint32_t)tid < e0 ? CLS_MISS : (uint32_t)tid < e1 ? CLS_DIFFUSE : (uint32_t)tid < e2 ? CLS_METAL : (uint32_t)tid < e3 ? CLS_GLASS : CLS_LIGHT);
+            bool done = false;
+            if (active) {
+                const D3 o = mk(s_ox[s], s_oy[s], s_oz[s]), d = mk(s_dx[s], s_dy[s], s_dz[s]);
+                uint32_t level = s_lvl[s];
+                const uint32_t rays_sample = level + 1u;   // hit_world calls of this path so far, this one included
+                float cr = 0.f, cg = 0.f, cb = 0.f;
+                if (c == CLS_MISS) {                                                // raytracer.rs:134-163
+                    sky_color(d, length(d), p.sky_mode, p.sky, cr, cg, cb);
+                    done = true;
+                } else if (c == CLS_LIGHT) {                                        // materials.rs:65-69
+                    cr = 1.f; cg = 1.f; cb = 1.f;
+                    done = true;
+                } else {
+                    const uint32_t best = s_bi[s];
+                    const double best_t = s_bt[s];
+                    double4 gq = geo[best];
+                    const D3 center = mk(gq.x, gq.y, gq.z);
+                    HitRec h = hit_record(center, gq.w, o, d, best_t);
+                    const DevMat m = mat[best];
+                    Rng rng; rng.pixel = s_pix[s]; rng.sample = s_smp[s];
+                    { uint32_t bh = s_blk[s]; rng.blk = bh >> 1; rng.has = bh & 1u; }
+                    rng.c_lo = s_clo[s]; rng.c_hi = s_chi[s];
+                    uint32_t code = best;
+                    D3 nd;
+                    bool scattered = true;
+                    if (c == CLS_DIFFUSE) {                                         // materials.rs:84-95, 256-267
+                        D3 rs = random_in_unit_sphere(rng, k0, k1);
+                        D3 sd = add(h.normal, rs);
+                        if (near_zero(sd)) sd = h.normal;
+                        D3 target = add(h.point, sd);
+                        nd = sub(target, h.point);
+                        if (m.kind == RT_TEXTURE) {
+                            double tu, tv;
+                            sphere_uv(sub(h.point, center), tu, tv);
+                            code = 0x80000000u | texture_texel(p.tex[m.tex], m.param, tu, tv);
+                        }
+                    } else if (c == CLS_METAL) {                                    // materials.rs:115-129
+                        D3 rs = random_in_unit_sphere(rng, k0, k1);
+                        D3 refl = reflect(d, h.normal);
+                        nd = add(refl, mul(rs, m.param));
+                        if (!(dot(nd, h.normal) > 0.0)) { scattered = false; done = true; }   // absorbed -> black
+                    } else {                                                        // Glass, materials.rs:176-199
+                        double ratio = h.front_face ? __ddiv_rn(1.0, m.param) : m.param;
+                        D3 ud = unit_vector(d);
+                        double cos_theta = fmin(dot(neg(ud), h.normal), 1.0);
+                        double sin_theta = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cos_theta, cos_theta)));
+                        bool refl = __dmul_rn(ratio, sin_theta) > 1.0;              // cannot_refract
+                        if (!refl) refl = reflectance(cos_theta, ratio) > rng_f64(rng, k0, k1);   // drawn only if refraction is possible
+                        nd = refl ? reflect(ud, h.normal) : refract(ud, h.normal, ratio);
+                    }
+                    if (scattered) {
+                        p.stack[(size_t)level * p.stack_stride + stack_col + s] = code;
+                        ++level;
+                        s_ox[s] = h.point.x; s_oy[s] = h.point.y; s_oz[s] = h.point.z;
+                        s_dx[s] = nd.x; s_dy[s] = nd.y; s_dz[s] = nd.z;
+                        s_blk[s] = (rng.blk << 1) | rng.has; s_clo[s] = rng.c_lo; s_chi[s] = rng.c_hi;
+                        s_lvl[s] = level;
+                        if (level == p.max_depth) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
+                    }
+                }
+                if (done) {
+                    // unwind the recursion: c = clamp(light + albedo * c) per level, innermost first (raytracer.rs:117-122)
+                    if (cr != 0.f || cg != 0.f || cb != 0.f) {
+                        for (int l = (int)level - 1; l >= 0; --l) {
+                            float ar, ag, ab;
+                            albedo_of(p.stack[(size_t)l * p.stack_stride + stack_col + s], mat, ar, ag, ab);
+                            cr = clampf(__fadd_rn(0.0f, __fmul_rn(ar, cr)));
+                            cg = clampf(__fadd_rn(0.0f, __fmul_rn(ag, cg)));
+                            cb = clampf(__fadd_rn(0.0f, __fmul_rn(ab, cb)));
+                        }
+                    }
+                    p.samplebuf[s_work[s]] = make_float4(cr, cg, cb, __uint_as_float(rays_sample));
+                    s_lvl[s] = kDeadLevel;
+                }
+            }
+            regenerate(active && done, s);
+            still_alive = active && (s_lvl[s] != kDeadLevel);
+        }
+        PF_MARK(pf_shade)
+        bool any_alive = __syncthreads_or(still_alive ? 1 : 0);
+        PF_MARK(pf_waitC)
+#ifdef RT_PROFILE_PHASES
+        ++pf_iters;
+#endif
+        if (!any_alive) break;   // C: pool written back; exit when the CTA has no ray left
+    }
+
+#ifdef RT_PROFILE_PHASES
+    if (lane == 0) {   // per-warp cycle totals of each phase
+        atomicAdd(&p.stat[8], pf_scan); atomicAdd(&p.stat[9], pf_confirm); atomicAdd(&p.stat[10], pf_waitA); atomicAdd(&p.stat[11], pf_sort);
+        atomicAdd(&p.stat[12], pf_shade); atomicAdd(&p.stat[13], pf_waitC); atomicAdd(&p.stat[14], pf_iters);
+    }
+#endif
+    // ---- statistics: one atomic per warp ----
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        st_rays += __shfl_down_sync(FULL, st_rays, off);
+        st_cand += __shfl_down_sync(FULL, st_cand, off);
+        st_ovf += __shfl_down_sync(FULL, st_ovf, off);
+        st_samples += __shfl_down_sync(FULL, st_samples, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.stat[0], st_rays);
+        atomicAdd(&p.stat[1], st_cand);
+        atomicAdd(&p.stat[2], st_ovf);
+        atomicAdd(&p.stat[3], st_samples);
+    }
+}
+
+template <int B, bool E>
+static cudaError_t launch_wf(const TraceParams& p, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rt_wavefront_kernel<B, E><<<grid, B, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st) {
+    if (block == 128) return exact ? launch_wf<128, true>(p, grid, smem, st) : launch_wf<128, false>(p, grid, smem, st);
+    return exact ? launch_wf<256, true>(p, grid, smem, st) : launch_wf<256, false>(p, grid, smem, st);
+}
+
+int wavefront_max_ctas_per_sm(size_t smem, int block) {
+    int nb = 0;
+    cudaError_t e;
+    if (block == 128) {
+        cudaFuncSetAttribute(rt_wavefront_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<128, false>, 128, smem);
+    } else {
+        cudaFuncSetAttribute(rt_wavefront_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false>, 256, smem);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+}
+
+}  // namespace rtk

@@ -106,10 +106,10 @@ def test_gpu_matches_committed_golden(name, mk):
     assert np.array_equal(lin, g["linear"]) and np.array_equal(img, g["rgb8"]) and st["rays"] == int(g["rays"])
 
 
-@pytest.mark.parametrize("variant", [R.RT_VARIANT_FILTERED, R.RT_VARIANT_EXACT_F64])
+@pytest.mark.parametrize("variant", [R.RT_VARIANT_FILTERED, R.RT_VARIANT_EXACT_F64, R.RT_VARIANT_LANES])
 def test_cover_scene_bit_exact(variant):
     st = _exact(scenes.cover_scene(200, 150, 8), R.make_options(variant=variant))
-    if variant == R.RT_VARIANT_FILTERED:
+    if variant != R.RT_VARIANT_EXACT_F64:
         assert st["candidates"] / st["rays"] < 8.0     # the f32 filter prunes >98 % of the 484 sphere tests
     else:
         assert st["candidates"] == st["rays"] * 484
@@ -118,6 +118,7 @@ def test_cover_scene_bit_exact(variant):
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_mixed_materials_bit_exact(seed):
     _exact(R.Scene.from_config(mixed_config(96, 72, 4, 20, seed=seed)))
+    _exact(R.Scene.from_config(mixed_config(96, 72, 4, 20, seed=seed)), R.make_options(variant=R.RT_VARIANT_LANES))
 
 
 @pytest.mark.parametrize("offset", [(1.0e3, 50.0, -2.0e3), (1.0e5, 0.0, 1.0e5), (-3.0e6, 1.0e3, 7.0e6)])

@@ -20,11 +20,13 @@ def cmp(name, sc, variant=0):
 sc = scenes.cover_scene(200, 150, 8)
 cmp("cover200x150x8", sc, R.RT_VARIANT_EXACT_F64)
 cmp("cover200x150x8", sc, R.RT_VARIANT_FILTERED)
+cmp("cover200x150x8", sc, R.RT_VARIANT_LANES)
 sc = scenes.cover_scene(64, 48, 4, depth=3)
 cmp("cover64x48 depth3", sc, R.RT_VARIANT_FILTERED)
 if len(sys.argv) > 1 and sys.argv[1] == 'time':
     sc = scenes.scene('C2')
-    rs = R.ResidentScene(sc)
+    variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rs = R.ResidentScene(sc, R.make_options(variant=variant))
     import torch
     out = torch.empty(sc.c.height*sc.c.width*3, dtype=torch.uint8, device='cuda')
     for i in range(4):
