@@ -272,6 +272,13 @@ def run_ours(args):
 
     n = scene.n_spheres
     hbm_peak, peak_src, sm_max = measured_peaks()
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram__bytes_read+write of one trace launch, from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("config") == args.config and world == 1:
+            traffic = tj.get("dram_bytes_per_launch")
     rays_per_launch = rays / args.steps            # rank 0's trace launch
     t_launch = (trace_ms / args.steps) / 1e3
     achieved = rays_per_launch * ALG_BYTES_PER_RAY / t_launch / 1e9
@@ -286,12 +293,12 @@ def run_ours(args):
                    "l2": "flushed (256 MiB device write) between steps, inside the timed region",
                    "timing": "CUDA events on the launching stream, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e_wall / args.steps * 1e3, "path": "rtb200_render_rgb8 (C ABI), pinned host buffers"},
+                "ms_per_step": e_wall / args.steps * 1e3, "path": "rtb200_render_rgb8 (C ABI), pinned host frame" if world == 1 else "per step: rtb200_scene_upload (H2D) + rtb200_render_device + NCCL gather + D2H of the frame on rank 0"},
         "gpu_launches": int(total_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "kernel": "rt_trace_kernel<false>", "peak_source": peak_src,
-                     "note": f"algorithmic {ALG_BYTES_PER_RAY:.0f} B/ray (SURVEY §8d wavefront record); the kernel keeps ray state in registers, "
-                             "so HBM is not the binding resource - see fp32_issue",
+                     "traffic": traffic, "kernel": "rt_wavefront_kernel<256,false>", "peak_source": peak_src,
+                     "note": f"algorithmic {ALG_BYTES_PER_RAY:.0f} B/ray (SURVEY §8d wavefront record) x rays per launch; the kernel keeps ray state in shared memory, "
+                             "so HBM is not the binding resource (traffic = ncu dram bytes of one launch) - the binding one is FP32 issue, see fp32_issue",
                      "kernel_ms_per_launch": t_launch * 1e3, "kernel_share_of_step": (trace_ms_max / args.steps) / step_ms},
         "fp32_issue": {"achieved": flops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / fp32_peak,
                        "flop_per_ray": FLOP_PER_SPHERE_TEST * n + FLOP_PER_RAY_FIXED,

@@ -7,6 +7,6 @@ TAG=${1:-r01}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # (2) the top kernel, full set, once
-ncu --set full --clock-control none --import-source on -k regex:rt_trace -s 1 -c 1 -f -o gpurun_out/trace_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:rt_wavefront -s 1 -c 1 -f -o gpurun_out/trace_${TAG} \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out
