@@ -51,7 +51,7 @@ struct DeviceCtx {
     int sm_count = 0;
     size_t max_smem = 0;
     cudaStream_t stream = nullptr;
-    GrowBuf samplebuf, accum, stack, small, out_rgb8, out_lin, probe;
+    GrowBuf samplebuf, accum, stack, small, out_rgb8, out_lin, probe, frames, lterm;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 };
@@ -206,7 +206,8 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
             if (!im.rgb8 || im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "empty texture image");
         }
     }
-    if (n_lights > 0) return fail(RT_ERR_UNSUPPORTED, "Light materials (shadow-ray recursion, raytracer.rs:89-114) are not built yet");
+    if (n_lights >= 10) return fail(RT_ERR_UNSUPPORTED, "10 or more lights: the reference's light recursion (raytracer.rs:99-114) does not terminate when n_lights * 0.1 >= 1");
+    if (n_lights > 0 && opts.variant == RT_VARIANT_LANES) return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES has no light support");
     if (s->sky.mode > RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "unknown sky mode");
     if (s->sky.mode == RT_SKY_TEXTURE && (!s->sky.tex.rgb8 || s->sky.tex.width == 0 || s->sky.tex.height == 0))
         return fail(RT_ERR_INVALID, "sky texture is empty");
@@ -296,6 +297,13 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         tp.sky.rgb8 = (const uint8_t*)d; tp.sky.width = s->sky.tex.width; tp.sky.height = s->sky.tex.height;
     }
 
+    {
+        std::vector<uint32_t> lights;
+        for (uint32_t i = 0; i < n; ++i) if (s->spheres[i].kind == RT_LIGHT) lights.push_back(i);
+        lights.push_back(0);
+        if ((rc = upload_array(h, lights.data(), lights.size() * 4, &d)) != RT_OK) return rc;
+        tp.lights = (const uint32_t*)d;
+    }
     tp.n = n; tp.n_pairs = n_pairs; tp.n_lights = n_lights;
     tp.gx = g[0]; tp.gy = g[1]; tp.gz = g[2];
     tp.er_coef = 1.0f - (float)(96.0 * U);
@@ -371,6 +379,17 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
     CU(ctx->accum.ensure((size_t)tp.npix_local * 12));
     CU(ctx->stack.ensure((size_t)std::max<uint32_t>(tp.max_depth, 1) * threads_total * 4));
     CU(ctx->small.ensure(256 + (size_t)n_batches * 4));
+    if (tp.n_lights > 0) {
+        // Nested light tests form a branching process: a vertex nests with probability 0.1 n and then spawns n shadow rays, so
+        // depth d is reached with probability ~(0.1 n^2 P_hit)^d: harmless for 1-2 lights, near-critical for 3 (the reference
+        // itself recurses hundreds of frames deep there) and super-critical beyond. Size the per-path frame stack accordingly;
+        // an overflow is reported as an error, never rendered wrongly.
+        tp.max_shadow = tp.n_lights == 1 ? 32u : tp.n_lights == 2 ? 96u : 384u;
+        CU(ctx->frames.ensure((size_t)tp.max_shadow * threads_total * sizeof(ShadowFrame)));
+        CU(ctx->lterm.ensure((size_t)6 * threads_total * 4));
+    }
+    tp.frames = (ShadowFrame*)ctx->frames.p;
+    tp.lterm = (float*)ctx->lterm.p;
     while (ctx->ev.size() < 2 * (size_t)n_batches) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
@@ -422,6 +441,7 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
             fprintf(stderr, "[rtb200] ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
                     hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
         }
+        if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
         if (tp.max_depth == 0) stats->samples = (uint64_t)tp.npix_local * spp;   // no kernel ran: every sample is black
         stats->kernel_launches = launches; stats->batches = n_batches;
         stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();

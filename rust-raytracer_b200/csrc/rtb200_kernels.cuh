@@ -20,6 +20,16 @@ constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory
 struct DevMat { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };
 static_assert(sizeof(DevMat) == 32, "DevMat must be 32 bytes");
 
+// One pending light test (raytracer.rs:99-114): the vertex it belongs to and the partial sum over the lights.
+struct ShadowFrame {
+    double px, py, pz;      // hit point = origin of the shadow rays and of the scattered ray
+    double ndx, ndy, ndz;   // scattered direction (continuation of the main path)
+    float ar, ag, ab;       // albedo of the vertex
+    float sr, sg, sb;       // sum over lights of albedo * ray_color(light_ray, 2, 1)
+    uint32_t li, code, is_light, pad;
+};
+static_assert(sizeof(ShadowFrame) == 88, "ShadowFrame layout");
+
 struct TraceParams {
     // scene, resident in HBM
     const float4*       filt;      // n_pairs*2 float4: {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}, recentred f32 filter records
@@ -46,7 +56,11 @@ struct TraceParams {
     float4*  samplebuf;            // [s_count][npix_local] per-sample radiance (w = rays of the sample)
     uint32_t* stack;               // [max_depth][stack_stride] per-lane albedo codes
     uint32_t stack_stride;
-    unsigned long long* stat;      // [0]=rays [1]=candidates [2]=overflows [3]=samples
+    const uint32_t* lights;        // sphere indices of the Light spheres in list order (find_lights, raytracer.rs:220-229)
+    ShadowFrame* frames;           // [max_shadow][stack_stride], only when n_lights > 0
+    uint32_t max_shadow;           // nested light-test frames per path (a level nests with probability <= n_lights*0.1)
+    float* lterm;                  // [2 levels][3][stack_stride] light terms of the first two path levels
+    unsigned long long* stat;      // [0]=rays [1]=candidates [2]=overflows [3]=samples [5]=shadow-stack overflows
 };
 
 struct ResolveParams {

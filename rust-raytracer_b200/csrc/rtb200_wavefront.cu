@@ -32,7 +32,7 @@ constexpr uint32_t kDeadLevel = 0xffffffffu;
 struct WfSmem {
     uint32_t filt_off, geo_off, mat_off, cand_off;
     uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each
-    uint32_t bi, work, pix, smp, blk, clo, chi, lvl;   // uint32[kBlock] each
+    uint32_t bi, work, pix, smp, blk, clo, chi, lvl, shd;   // uint32[kBlock] each
     uint32_t perm;                                  // uint16[kBlock]
     uint32_t cnt;                                   // uint32[2][8]
     uint32_t flags;                                 // uint32[4]
@@ -50,7 +50,7 @@ __host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, bool s
     L.dx = off; off += kBlock * 8u; L.dy = off; off += kBlock * 8u; L.dz = off; off += kBlock * 8u;
     L.bt = off; off += kBlock * 8u;
     L.bi = off; off += kBlock * 4u; L.work = off; off += kBlock * 4u; L.pix = off; off += kBlock * 4u; L.smp = off; off += kBlock * 4u;
-    L.blk = off; off += kBlock * 4u; L.clo = off; off += kBlock * 4u; L.chi = off; off += kBlock * 4u; L.lvl = off; off += kBlock * 4u;
+    L.blk = off; off += kBlock * 4u; L.clo = off; off += kBlock * 4u; L.chi = off; off += kBlock * 4u; L.lvl = off; off += kBlock * 4u; L.shd = off; off += kBlock * 4u;
     L.perm = off; off += kBlock * 2u;
     L.cnt = off; off += 2u * 8u * 4u;
     L.flags = off; off += 16u;
@@ -67,6 +67,7 @@ RT_DEV void bulk_stage(void* dst, const void* src, uint32_t bytes, uint64_t* bar
 }
 
 RT_DEV void albedo_of(uint32_t code, const DevMat* mat, float& r, float& g, float& b) {
+    if (code == 0xffffffffu) { r = g = b = 1.0f; return; }   // Light: Srgb(1,1,1) (materials.rs:67)
     if (code & 0x80000000u) {   // packed texel (materials.rs:248-252: pixel as f32 / 255.0)
         r = __fdiv_rn((float)(code & 0xffu), 255.0f);
         g = __fdiv_rn((float)((code >> 8) & 0xffu), 255.0f);
@@ -81,7 +82,7 @@ RT_DEV void albedo_of(uint32_t code, const DevMat* mat, float& r, float& g, floa
 
 size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem, int block) { return wf_layout(n, n_pairs, scene_in_smem, (uint32_t)block).total; }
 
-template <int kBlock, bool EXACT>
+template <int kBlock, bool EXACT, bool LIGHTS>
 __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WfSmem L = wf_layout(p.n, p.n_pairs, p.scene_in_smem != 0, kBlock);
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     uint32_t* s_pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix); uint32_t* s_smp = reinterpret_cast<uint32_t*>(smem_raw + L.smp);
     uint32_t* s_blk = reinterpret_cast<uint32_t*>(smem_raw + L.blk); uint32_t* s_clo = reinterpret_cast<uint32_t*>(smem_raw + L.clo);
     uint32_t* s_chi = reinterpret_cast<uint32_t*>(smem_raw + L.chi); uint32_t* s_lvl = reinterpret_cast<uint32_t*>(smem_raw + L.lvl);
+    uint32_t* s_shd = reinterpret_cast<uint32_t*>(smem_raw + L.shd);   // depth of the shadow-frame stack (0 = main path)
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + L.perm);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + L.cnt);
     volatile uint32_t* s_flags = reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags);   // [0] = queue exhausted
@@ -162,6 +164,10 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
         s_work[s] = my; s_pix[s] = rng.pixel; s_smp[s] = rng.sample;
         s_blk[s] = (rng.blk << 1) | rng.has; s_clo[s] = rng.c_lo; s_chi[s] = rng.c_hi;
         s_lvl[s] = 0u;
+        if (LIGHTS) {
+            s_shd[s] = 0u;
+            for (int q = 0; q < 6; ++q) p.lterm[(size_t)q * p.stack_stride + stack_col + s] = 0.0f;
+        }
         ++st_samples;
     };
 
@@ -296,16 +302,22 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
             const uint32_t c = !active ? CLS_DEAD : ((uint32_t)tid < e0 ? CLS_MISS : (uint32_t)tid < e1 ? CLS_DIFFUSE : (uint32_t)tid < e2 ? CLS_METAL : (uint32_t)tid < e3 ? CLS_GLASS : CLS_LIGHT);
             bool done = false;
             if (active) {
-                const D3 o = mk(s_ox[s], s_oy[s], s_oz[s]), d = mk(s_dx[s], s_dy[s], s_dz[s]);
+                D3 o = mk(s_ox[s], s_oy[s], s_oz[s]), d = mk(s_dx[s], s_dy[s], s_dz[s]);
                 uint32_t level = s_lvl[s];
-                const uint32_t rays_sample = level + 1u;   // hit_world calls of this path so far, this one included
+                uint32_t shd = LIGHTS ? s_shd[s] : 0u;       // > 0: this ray is a shadow ray of the light test (raytracer.rs:103-106)
+                const uint32_t rays_sample = level + 1u;   // main-path hit_world calls so far, this one included
                 float cr = 0.f, cg = 0.f, cb = 0.f;
+                bool have_tc = false;                      // a shadow ray's ray_color(.., 2, 1) value is ready
+                float tr = 0.f, tg = 0.f, tb = 0.f;
+                bool state_dirty = false;                  // o/d/rng/level must be written back to the pool
+                Rng rng; rng.pixel = s_pix[s]; rng.sample = s_smp[s];
+                { uint32_t bh = s_blk[s]; rng.blk = bh >> 1; rng.has = bh & 1u; }
+                rng.c_lo = s_clo[s]; rng.c_hi = s_chi[s];
                 if (c == CLS_MISS) {                                                // raytracer.rs:134-163
-                    sky_color(d, length(d), p.sky_mode, p.sky, cr, cg, cb);
-                    done = true;
-                } else if (c == CLS_LIGHT) {                                        // materials.rs:65-69
-                    cr = 1.f; cg = 1.f; cb = 1.f;
-                    done = true;
+                    float x, y, z;
+                    sky_color(d, length(d), p.sky_mode, p.sky, x, y, z);
+                    if (shd == 0u) { cr = x; cg = y; cb = z; done = true; }
+                    else { tr = x; tg = y; tb = z; have_tc = true; }
                 } else {
                     const uint32_t best = s_bi[s];
                     const double best_t = s_bt[s];
@@ -313,12 +325,10 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                     const D3 center = mk(gq.x, gq.y, gq.z);
                     HitRec h = hit_record(center, gq.w, o, d, best_t);
                     const DevMat m = mat[best];
-                    Rng rng; rng.pixel = s_pix[s]; rng.sample = s_smp[s];
-                    { uint32_t bh = s_blk[s]; rng.blk = bh >> 1; rng.has = bh & 1u; }
-                    rng.c_lo = s_clo[s]; rng.c_hi = s_chi[s];
                     uint32_t code = best;
-                    D3 nd;
-                    bool scattered = true;
+                    D3 nd = d;
+                    bool absorbed = false;
+                    const bool is_light = (c == CLS_LIGHT);                         // materials.rs:65-69: Some((None, white))
                     if (c == CLS_DIFFUSE) {                                         // materials.rs:84-95, 256-267
                         D3 rs = random_in_unit_sphere(rng, k0, k1);
                         D3 sd = add(h.normal, rs);
@@ -334,8 +344,8 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                         D3 rs = random_in_unit_sphere(rng, k0, k1);
                         D3 refl = reflect(d, h.normal);
                         nd = add(refl, mul(rs, m.param));
-                        if (!(dot(nd, h.normal) > 0.0)) { scattered = false; done = true; }   // absorbed -> black
-                    } else {                                                        // Glass, materials.rs:176-199
+                        if (!(dot(nd, h.normal) > 0.0)) absorbed = true;            // None -> black, no light test (raytracer.rs:127-131)
+                    } else if (c == CLS_GLASS) {                                    // materials.rs:176-199
                         double ratio = h.front_face ? __ddiv_rn(1.0, m.param) : m.param;
                         D3 ud = unit_vector(d);
                         double cos_theta = fmin(dot(neg(ud), h.normal), 1.0);
@@ -344,25 +354,102 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                         if (!refl) refl = reflectance(cos_theta, ratio) > rng_f64(rng, k0, k1);   // drawn only if refraction is possible
                         nd = refl ? reflect(ud, h.normal) : refract(ud, h.normal, ratio);
                     }
-                    if (scattered) {
-                        p.stack[(size_t)level * p.stack_stride + stack_col + s] = code;
-                        ++level;
-                        s_ox[s] = h.point.x; s_oy[s] = h.point.y; s_oz[s] = h.point.z;
-                        s_dx[s] = nd.x; s_dy[s] = nd.y; s_dz[s] = nd.z;
-                        s_blk[s] = (rng.blk << 1) | rng.has; s_clo[s] = rng.c_lo; s_chi[s] = rng.c_hi;
-                        s_lvl[s] = level;
-                        if (level == p.max_depth) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
+                    state_dirty = true;
+                    if (absorbed) {
+                        if (shd == 0u) done = true;            // main path ends black
+                        else have_tc = true;                   // the shadow ray returns black
+                    } else {
+                        // ---- light test, raytracer.rs:89-101 (the uniform is drawn whenever the scene has lights) ----
+                        bool pass = false;
+                        if (LIGHTS) {
+                            const double prob = (c == CLS_GLASS) ? 0.05 : 0.1;
+                            const double xi = rng_f64(rng, k0, k1);
+                            const unsigned long long depth_now = (unsigned long long)p.max_depth - level;
+                            const bool depth_ok = (shd > 0u) ? true : (depth_now > (unsigned long long)p.max_depth - 2ull);   // usize wrap like a release build
+                            pass = (xi > __dsub_rn(1.0, __dmul_rn((double)p.n_lights, prob))) && depth_ok;
+                            if (pass && shd >= p.max_shadow) { pass = false; atomicAdd(&p.stat[5], 1ull); }   // reported as an error by the host
+                        }
+                        if (pass) {
+                            float ar, ag, ab;
+                            albedo_of(is_light ? 0xffffffffu : code, mat, ar, ag, ab);
+                            ShadowFrame f;
+                            f.px = h.point.x; f.py = h.point.y; f.pz = h.point.z; f.ndx = nd.x; f.ndy = nd.y; f.ndz = nd.z;
+                            f.ar = ar; f.ag = ag; f.ab = ab; f.sr = 0.f; f.sg = 0.f; f.sb = 0.f; f.li = 0u; f.code = code; f.is_light = is_light ? 1u : 0u; f.pad = 0u;
+                            p.frames[(size_t)shd * p.stack_stride + stack_col + s] = f;
+                            ++shd;
+                            double4 lq = geo[p.lights[0]];
+                            o = h.point; d = sub(mk(lq.x, lq.y, lq.z), h.point);   // Ray::new(point, light.center - point)
+                        } else if (shd == 0u) {
+                            if (is_light) { cr = 1.f; cg = 1.f; cb = 1.f; done = true; }   // `None => albedo` (raytracer.rs:124)
+                            else {
+                                p.stack[(size_t)level * p.stack_stride + stack_col + s] = code;
+                                ++level;
+                                o = h.point; d = nd;
+                                if (level == p.max_depth) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
+                            }
+                        } else {
+                            // nested vertex without light contribution: clamp(0 + albedo * black), or white for a Light
+                            tr = tg = tb = is_light ? 1.f : 0.f;
+                            have_tc = true;
+                        }
                     }
+                }
+                if (LIGHTS) {
+                    // return values travel up the shadow-frame stack without tracing (raytracer.rs:103-114)
+                    while (have_tc) {
+                        ShadowFrame f = p.frames[(size_t)(shd - 1u) * p.stack_stride + stack_col + s];
+                        f.sr = __fadd_rn(f.sr, __fmul_rn(f.ar, tr)); f.sg = __fadd_rn(f.sg, __fmul_rn(f.ag, tg)); f.sb = __fadd_rn(f.sb, __fmul_rn(f.ab, tb));
+                        ++f.li;
+                        state_dirty = true;
+                        if (f.li < p.n_lights) {                                   // next light of the same vertex
+                            p.frames[(size_t)(shd - 1u) * p.stack_stride + stack_col + s] = f;
+                            double4 lq = geo[p.lights[f.li]];
+                            o = mk(f.px, f.py, f.pz); d = sub(mk(lq.x, lq.y, lq.z), o);
+                            have_tc = false;
+                        } else {
+                            const float nl = (float)p.n_lights;
+                            const float Lr = __fdiv_rn(f.sr, nl), Lg = __fdiv_rn(f.sg, nl), Lb = __fdiv_rn(f.sb, nl);
+                            --shd;
+                            if (shd == 0u) {                                        // back on the main path
+                                have_tc = false;
+                                if (f.is_light) { cr = 1.f; cg = 1.f; cb = 1.f; done = true; }
+                                else {
+                                    p.lterm[(size_t)(level * 3u + 0u) * p.stack_stride + stack_col + s] = Lr;   // level is 0 or 1 here
+                                    p.lterm[(size_t)(level * 3u + 1u) * p.stack_stride + stack_col + s] = Lg;
+                                    p.lterm[(size_t)(level * 3u + 2u) * p.stack_stride + stack_col + s] = Lb;
+                                    p.stack[(size_t)level * p.stack_stride + stack_col + s] = f.code;
+                                    ++level;
+                                    o = mk(f.px, f.py, f.pz); d = mk(f.ndx, f.ndy, f.ndz);
+                                    if (level == p.max_depth) done = true;
+                                }
+                            } else if (f.is_light) { tr = tg = tb = 1.f; }
+                            else {                                                  // clamp(light + albedo * ray_color(depth 0) = black)
+                                tr = clampf(__fadd_rn(Lr, __fmul_rn(f.ar, 0.0f))); tg = clampf(__fadd_rn(Lg, __fmul_rn(f.ag, 0.0f))); tb = clampf(__fadd_rn(Lb, __fmul_rn(f.ab, 0.0f)));
+                            }
+                        }
+                    }
+                }
+                if (state_dirty && !done) {
+                    s_ox[s] = o.x; s_oy[s] = o.y; s_oz[s] = o.z; s_dx[s] = d.x; s_dy[s] = d.y; s_dz[s] = d.z;
+                    s_blk[s] = (rng.blk << 1) | rng.has; s_clo[s] = rng.c_lo; s_chi[s] = rng.c_hi;
+                    s_lvl[s] = level;
+                    if (LIGHTS) s_shd[s] = shd;
                 }
                 if (done) {
                     // unwind the recursion: c = clamp(light + albedo * c) per level, innermost first (raytracer.rs:117-122)
-                    if (cr != 0.f || cg != 0.f || cb != 0.f) {
+                    if (LIGHTS || cr != 0.f || cg != 0.f || cb != 0.f) {
                         for (int l = (int)level - 1; l >= 0; --l) {
                             float ar, ag, ab;
                             albedo_of(p.stack[(size_t)l * p.stack_stride + stack_col + s], mat, ar, ag, ab);
-                            cr = clampf(__fadd_rn(0.0f, __fmul_rn(ar, cr)));
-                            cg = clampf(__fadd_rn(0.0f, __fmul_rn(ag, cg)));
-                            cb = clampf(__fadd_rn(0.0f, __fmul_rn(ab, cb)));
+                            float Lr = 0.f, Lg = 0.f, Lb = 0.f;
+                            if (LIGHTS && l < 2) {
+                                Lr = p.lterm[(size_t)(l * 3 + 0) * p.stack_stride + stack_col + s];
+                                Lg = p.lterm[(size_t)(l * 3 + 1) * p.stack_stride + stack_col + s];
+                                Lb = p.lterm[(size_t)(l * 3 + 2) * p.stack_stride + stack_col + s];
+                            }
+                            cr = clampf(__fadd_rn(Lr, __fmul_rn(ar, cr)));
+                            cg = clampf(__fadd_rn(Lg, __fmul_rn(ag, cg)));
+                            cb = clampf(__fadd_rn(Lb, __fmul_rn(ab, cb)));
                         }
                     }
                     p.samplebuf[s_work[s]] = make_float4(cr, cg, cb, __uint_as_float(rays_sample));
@@ -403,28 +490,30 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     }
 }
 
-template <int B, bool E>
+template <int B, bool E, bool LI>
 static cudaError_t launch_wf(const TraceParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E, LI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rt_wavefront_kernel<B, E><<<grid, B, smem, st>>>(p);
+    rt_wavefront_kernel<B, E, LI><<<grid, B, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st) {
-    if (block == 128) return exact ? launch_wf<128, true>(p, grid, smem, st) : launch_wf<128, false>(p, grid, smem, st);
-    return exact ? launch_wf<256, true>(p, grid, smem, st) : launch_wf<256, false>(p, grid, smem, st);
+    const bool li = p.n_lights > 0;
+    if (block == 128) return exact ? launch_wf<128, true, false>(p, grid, smem, st) : launch_wf<128, false, false>(p, grid, smem, st);
+    if (li) return exact ? launch_wf<256, true, true>(p, grid, smem, st) : launch_wf<256, false, true>(p, grid, smem, st);
+    return exact ? launch_wf<256, true, false>(p, grid, smem, st) : launch_wf<256, false, false>(p, grid, smem, st);
 }
 
 int wavefront_max_ctas_per_sm(size_t smem, int block) {
     int nb = 0;
     cudaError_t e;
     if (block == 128) {
-        cudaFuncSetAttribute(rt_wavefront_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<128, false>, 128, smem);
+        cudaFuncSetAttribute(rt_wavefront_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<128, false, false>, 128, smem);
     } else {
-        cudaFuncSetAttribute(rt_wavefront_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false>, 256, smem);
+        cudaFuncSetAttribute(rt_wavefront_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false, true>, 256, smem);
     }
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
