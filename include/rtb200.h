@@ -150,6 +150,11 @@ int rtb200_scene_upload(const rt_scene* scene, const rt_options* opts, rtb200_sc
 int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream, rt_stats* stats);
 int rtb200_scene_release(rtb200_scene_handle h);
 
+/* load_texture_image — materials.rs:213-219, config.rs:36-47: decode a baseline JPEG file to RGB8 (host-side scene staging
+ * helper for hosts without their own decoder; the reference uses the jpeg-decoder crate). *out_rgb8 is released with rtb200_free(). */
+int  rtb200_decode_jpeg_file(const char* path, uint8_t** out_rgb8, uint64_t* width, uint64_t* height);
+void rtb200_free(void* p);
+
 /* Device-function probes: run the kernel's own device routines on one thread and return the result,
  * so the reference's known-answer tests can be asserted against the GPU code itself.
  *   sphere.rs:81-88, materials.rs:157-174, raytracer.rs:167-189, camera.rs:105-122 */

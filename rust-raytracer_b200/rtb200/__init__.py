@@ -92,6 +92,7 @@ ABI_SYMBOLS = [
     "rtb200_render_rgb8", "rtb200_render_linear_f32", "rtb200_scene_upload", "rtb200_render_device",
     "rtb200_scene_release", "rtb200_probe_sphere_hit", "rtb200_probe_refract", "rtb200_probe_reflectance",
     "rtb200_probe_sky", "rtb200_probe_get_ray", "rtb200_probe_rng", "rtb200_probe_quantise",
+    "rtb200_decode_jpeg_file", "rtb200_free",
 ]
 
 _lib = None
@@ -124,6 +125,9 @@ def lib() -> C.CDLL:
     L.rtb200_probe_get_ray.argtypes = [C.POINTER(rt_camera), C.c_double, C.c_double, C.POINTER(rt_vec3), C.POINTER(rt_vec3)]
     L.rtb200_probe_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     L.rtb200_probe_quantise.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.rtb200_decode_jpeg_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.rtb200_free.argtypes = [C.c_void_p]
+    L.rtb200_free.restype = None
     _lib = L
     return L
 
@@ -157,10 +161,17 @@ def shard_row_indices(height: int, rank: int, world: int, band_rows: int = 1) ->
 
 
 def _decode_jpeg(path: str) -> np.ndarray:
-    from PIL import Image  # host-side texture decode (reference: jpeg-decoder, materials.rs:213-219)
-
-    with Image.open(path) as im:
-        return np.ascontiguousarray(np.asarray(im.convert("RGB"), dtype=np.uint8))
+    """load_texture_image (reference materials.rs:213-219): the library's own baseline JPEG decoder, so the Python host
+    and the C++ CLI stage identical texels."""
+    buf = C.c_void_p(); w = C.c_uint64(); h = C.c_uint64()
+    rc = lib().rtb200_decode_jpeg_file(os.fsencode(path), C.byref(buf), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise RtError(rc, f"cannot decode JPEG {path}")
+    try:
+        arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 3)).copy()
+    finally:
+        lib().rtb200_free(buf)
+    return arr
 
 
 class Scene:

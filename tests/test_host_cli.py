@@ -1,0 +1,95 @@
+"""The drop-in CLI `raytracer <config_file> <output_file>` (reference main.rs:7-20) and the host-side scene staging."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import rtb200 as R
+from rtb200 import scenes
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(REPO, "rust-raytracer_b200", "raytracer")
+
+
+def _run(args, **kw):
+    return subprocess.run([CLI] + args, capture_output=True, text=True, timeout=300, **kw)
+
+
+def test_usage_line_when_argc_is_not_3():
+    for args in ([], ["a"], ["a", "b", "c"]):
+        r = _run(args)
+        assert r.returncode == 0 and r.stdout == f"Usage: {CLI} <config_file> <output_file>\n"     # main.rs:9-12
+
+
+def test_unreadable_or_invalid_config_exits_like_a_panic(tmp_path):
+    r = _run([str(tmp_path / "missing.json"), str(tmp_path / "o.png")])
+    assert r.returncode == 101 and "Unable to read config file" in r.stderr                          # main.rs:14
+    bad = tmp_path / "bad.json"; bad.write_text('{"width": 10, "height": ')
+    r = _run([str(bad), str(tmp_path / "o.png")])
+    assert r.returncode == 101 and "Unable to parse config json" in r.stderr                          # main.rs:15
+    cfg = scenes._variant(scenes.cover_config(), 8, 6, 1, 2); cfg["objects"][1]["material"] = {"Plastic": {}}
+    bad.write_text(json.dumps(cfg))
+    r = _run([str(bad), str(tmp_path / "o.png")])
+    assert r.returncode == 101 and "unknown variant `Plastic`" in r.stderr
+    del cfg["objects"][1]["material"]; bad.write_text(json.dumps(cfg))
+    r = _run([str(bad), str(tmp_path / "o.png")])
+    assert r.returncode == 101 and "missing field `material`" in r.stderr
+
+
+def test_jpeg_decoder_agrees_with_libjpeg_within_rounding():
+    from PIL import Image
+    for name in ("earth.jpg", "beach.jpg"):      # 4:4:4 with Adobe marker; 4:2:0 with restart intervals
+        path = os.path.join(scenes.SCENES_DIR, "data", name)
+        a = R._decode_jpeg(path).astype(int)
+        b = np.asarray(Image.open(path).convert("RGB")).astype(int)
+        assert a.shape == b.shape
+        d = np.abs(a - b)
+        assert d.max() <= 4 and d.mean() < 0.3
+    assert R._decode_jpeg(os.path.join(scenes.SCENES_DIR, "data", "earth.jpg")).shape == (1024, 2048, 3)   # config.rs:135-146
+
+
+def test_scene_json_schema_strings_of_the_reference_tests(tmp_path):
+    """The literal JSON strings the reference's serialisation tests pin (config.rs:101,128; sphere.rs:101; camera.rs:134)
+    parse into the same scene through the Python host mirror."""
+    s1 = '{"width":100,"height":100,"samples_per_pixel":1,"max_depth":1,"sky":{"texture":""},"camera":{"look_from":{"x":0.0,"y":0.0,"z":0.0},"look_at":{"x":0.0,"y":0.0,"z":-1.0},"vup":{"x":0.0,"y":1.0,"z":0.0},"vfov":90.0,"aspect":1.0},"objects":[{"center":{"x":0.0,"y":0.0,"z":-1.0},"radius":0.5,"material":{"Lambertian":{"albedo":[0.8,0.3,0.3]}}}]}'
+    sc = R.Scene.from_config(json.loads(s1))
+    assert (sc.c.width, sc.c.height, sc.c.samples_per_pixel, sc.c.max_depth, sc.n_spheres, sc.c.sky.mode) == (100, 100, 1, 1, 1, R.RT_SKY_GRADIENT)
+    assert list(sc._spheres[0].albedo) == [np.float32(0.8), np.float32(0.3), np.float32(0.3)]
+    s2 = s1.replace('"sky":{"texture":""}', '"sky":null')
+    assert R.Scene.from_config(json.loads(s2)).c.sky.mode == R.RT_SKY_NONE                     # config.rs:128 + raytracer.rs:138-140
+    s3 = s1.replace('"sky":{"texture":""}', '"sky":{"texture":"data/earth.jpg"}')
+    sk = R.Scene.from_config(json.loads(s3), scenes.SCENES_DIR).c.sky
+    assert (sk.mode, sk.tex.width, sk.tex.height) == (R.RT_SKY_TEXTURE, 2048, 1024)         # config.rs:131-146
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_cli_without_gpu_fails_loudly(tmp_path):
+    p = tmp_path / "s.json"; p.write_text(json.dumps(scenes._variant(scenes.cover_config(), 16, 12, 1, 4)))
+    r = _run([str(p), str(tmp_path / "o.png")])
+    assert r.returncode == 101 and "render failed" in r.stderr and not (tmp_path / "o.png").exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["cover", "test_scene"])
+def test_cli_renders_the_same_png_as_the_python_host(tmp_path, which):
+    from PIL import Image
+    cfg = scenes._variant(scenes.cover_config(), 96, 72, 4, 12) if which == "cover" else scenes._variant(scenes.test_scene_config(), 80, 60, 4, 6)
+    p = tmp_path / "scene.json"; p.write_text(json.dumps(cfg))
+    out = tmp_path / "out.png"
+    r = _run([str(p), str(out)], cwd=scenes.SCENES_DIR)           # texture paths are relative to the CWD (materials.rs:214)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    assert lines[0] == "" and lines[1] == f"Rendering {out}" and lines[2].startswith("Frame time: ") and lines[2].endswith("ms")   # main.rs:18, raytracer.rs:263
+    png = np.asarray(Image.open(out))
+    ref, _ = R.render_rgb8(R.Scene.from_config(cfg, scenes.SCENES_DIR))
+    assert png.shape == (cfg["height"], cfg["width"], 3) and np.array_equal(png, ref)
