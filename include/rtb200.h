@@ -85,9 +85,10 @@ typedef struct {
 
 enum rt_trace_variant {
     RT_VARIANT_AUTO      = 0,
-    RT_VARIANT_FILTERED  = 1, /* CTA-wavefront kernel: f32 conservative filter + exact f64 confirmation (default) */
+    RT_VARIANT_FILTERED  = 1, /* CTA-wavefront kernel: two-level f32 conservative filter + exact f64 confirmation (default) */
     RT_VARIANT_EXACT_F64 = 2, /* every sphere tested in f64 (validation of the filter)        */
-    RT_VARIANT_LANES     = 3  /* lane-autonomous persistent kernel (no CTA-level sorting); kept for comparison */
+    RT_VARIANT_LANES     = 3, /* lane-autonomous persistent kernel (no CTA-level sorting); kept for comparison */
+    RT_VARIANT_BRUTE_FORCE = 4 /* CTA-wavefront kernel scanning every sphere (no cluster culling), like the reference's hit_world */
 };
 
 /* Which rows this call renders. Row-band b (band_rows consecutive rows) belongs to shard
@@ -112,6 +113,7 @@ typedef struct {
     uint32_t kernel_launches;
     uint32_t batches;
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t clusters;      /* second-level blocks visited (two-level culling; diagnostic) */
 } rt_stats;
 
 enum rt_status {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -220,7 +221,7 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     h->device = ctx->device; h->ctx = ctx; h->opts = opts;
     h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
     h->lanes = (opts.variant == RT_VARIANT_LANES);
-    if (opts.variant > RT_VARIANT_LANES) return fail(RT_ERR_INVALID, "unknown variant");
+    if (opts.variant > RT_VARIANT_BRUTE_FORCE) return fail(RT_ERR_INVALID, "unknown variant");
     struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
 
     // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
@@ -270,10 +271,127 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         }
     }
 
+    // ---- two-level culling (N4): spheres grouped into clusters of 8 with bounding spheres ----------------------------
+    // The cluster bound is tested with the SAME conservative 7-FMA filter as a sphere (a bounding sphere is a sphere),
+    // so culling stays a superset of what the exact f64 test can accept; results are identical by construction.
+    // Spheres are grouped by radius octave, then by Morton order of their centres; classes with <= 2 members and
+    // non-finite spheres become singleton clusters. Cluster k owns sphere-record slots [8k, 8k+8) (padded with
+    // never-hit records); orig[] maps a slot back to the sphere index (ties still go to the lowest ORIGINAL index).
+    auto make_record = [&](double x, double y, double z, double r2, float rec[4]) {
+        double c2 = x * x + y * y + z * z;
+        double Es = 96.0 * U * c2 + 16.0 * U * r2 + 1e-30;
+        double nkd = -(c2 - r2) + Es;
+        rec[0] = (float)x; rec[1] = (float)y; rec[2] = (float)z;
+        rec[3] = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
+        if (!(std::isfinite(rec[0]) && std::isfinite(rec[1]) && std::isfinite(rec[2])) || !(c2 < 1e30)) { rec[0] = rec[1] = rec[2] = 0.f; rec[3] = INFINITY; }
+    };
+    bool two_level = n > 32 && !h->lanes && !h->exact;
+    if (const char* e2 = getenv("RTB200_TWO_LEVEL")) two_level = two_level && atoi(e2) != 0;
+    if (opts.variant == RT_VARIANT_BRUTE_FORCE) two_level = false;
+    std::vector<float> cfilt, sfilt;
+    std::vector<uint16_t> orig;
+    std::vector<float> cmeta;
+    uint32_t n_clusters = 0, n_cpairs = 0;
+    if (two_level) {
+        constexpr int K = kClusterK;
+        std::vector<std::vector<uint32_t>> clusters;
+        std::map<int, std::vector<uint32_t>> classes;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rt_sphere& sp = s->spheres[i];
+            bool fin = std::isfinite(sp.center.x) && std::isfinite(sp.center.y) && std::isfinite(sp.center.z) && std::isfinite(sp.radius);
+            if (!fin || sp.radius == 0.0) { clusters.push_back({i}); continue; }
+            classes[std::ilogb(std::fabs(sp.radius))].push_back(i);
+        }
+        for (auto& kv : classes) {
+            std::vector<uint32_t>& mem = kv.second;
+            if (mem.size() <= 2) { for (uint32_t i : mem) clusters.push_back({i}); continue; }
+            // top-down median split on the widest axis until a leaf holds <= K spheres: compact leaves of K/2..K members
+            std::vector<std::pair<size_t, size_t>> work{{0, mem.size()}};
+            auto coord = [&](uint32_t i, int a) { return a == 0 ? s->spheres[i].center.x : a == 1 ? s->spheres[i].center.y : s->spheres[i].center.z; };
+            while (!work.empty()) {
+                auto [b0, e0] = work.back(); work.pop_back();
+                if (e0 - b0 <= (size_t)K) { clusters.emplace_back(mem.begin() + b0, mem.begin() + e0); continue; }
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                for (size_t t = b0; t < e0; ++t) for (int a = 0; a < 3; ++a) { double v = coord(mem[t], a); lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+                int ax = 0;
+                for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
+                // split so that both halves are multiples of K where possible (fewer padded slots)
+                size_t cnt = e0 - b0, half = ((cnt / 2 + K - 1) / K) * K;
+                if (half >= cnt) half = cnt / 2;
+                std::nth_element(mem.begin() + b0, mem.begin() + b0 + half, mem.begin() + e0, [&](uint32_t x, uint32_t y) { double cx = coord(x, ax), cy = coord(y, ax); return cx < cy || (cx == cy && x < y); });
+                work.emplace_back(b0, b0 + half); work.emplace_back(b0 + half, e0);
+            }
+        }
+        while (clusters.size() % 4 != 0) clusters.push_back({});   // keep every per-cluster array a multiple of 16 bytes (TMA bulk copies)
+        n_clusters = (uint32_t)clusters.size();
+        n_cpairs = ((n_clusters + 1) / 2 + 7) / 8 * 8;
+        cfilt.assign((size_t)n_cpairs * 8, 0.f);
+        sfilt.assign((size_t)n_clusters * K * 4, 0.f);    // K records = K/2 pairs = K float4 per cluster
+        orig.assign((size_t)n_clusters * K, 0xffff);
+        cmeta.assign(n_clusters, 0.f);
+        for (uint32_t pp = 0; pp < n_cpairs; ++pp) { float* A = &cfilt[(size_t)pp * 8]; A[6] = A[7] = -INFINITY; }
+        for (uint32_t k = 0; k < n_clusters; ++k) {
+            const std::vector<uint32_t>& cl = clusters[k];
+            if (cl.empty()) {   // padding cluster: never hit
+                float* A = &cfilt[(size_t)(k / 2) * 8]; int kk = k & 1; A[0 + kk] = A[2 + kk] = A[4 + kk] = 0.f; A[6 + kk] = -INFINITY;
+                for (int j = 0; j < K; ++j) { float* B = &sfilt[(size_t)k * K * 4 + (size_t)(j / 2) * 8]; B[6 + (j & 1)] = -INFINITY; }
+                continue;
+            }
+            // bounding sphere: centroid + max(|ci - c| + |ri|), inflated; non-finite members make the cluster "always hit"
+            double c[3] = {0, 0, 0};
+            bool fin = true;
+            for (uint32_t i : cl) { c[0] += s->spheres[i].center.x; c[1] += s->spheres[i].center.y; c[2] += s->spheres[i].center.z; }
+            for (int a = 0; a < 3; ++a) c[a] /= (double)cl.size();
+            double R = 0;
+            for (uint32_t i : cl) {
+                const rt_sphere& sp = s->spheres[i];
+                double dx = sp.center.x - c[0], dy = sp.center.y - c[1], dz = sp.center.z - c[2];
+                double dist = std::sqrt(dx * dx + dy * dy + dz * dz) + std::fabs(sp.radius);
+                if (!std::isfinite(dist)) fin = false;
+                R = std::max(R, dist);
+            }
+            R = R * (1.0 + 1e-9) + 1e-12;
+            float rec[4];
+            if (fin) make_record(c[0] - g[0], c[1] - g[1], c[2] - g[2], R * R, rec);
+            else { rec[0] = rec[1] = rec[2] = 0.f; rec[3] = INFINITY; }
+            { float* A = &cfilt[(size_t)(k / 2) * 8]; int kk = k & 1; A[0 + kk] = rec[0]; A[2 + kk] = rec[1]; A[4 + kk] = rec[2]; A[6 + kk] = rec[3]; }
+            {
+                double cx = c[0] - g[0], cy = c[1] - g[1], cz = c[2] - g[2];
+                double cn = std::sqrt(cx * cx + cy * cy + cz * cz);
+                cmeta[k] = (fin && std::isfinite(cn) && cn < 1e15) ? f32_up(cn * (1.0 + 1e-6)) : INFINITY;   // INFINITY disables the behind-origin cull
+            }
+            for (int j = 0; j < K; ++j) {
+                float r4[4] = {0.f, 0.f, 0.f, -INFINITY};
+                if (j < (int)cl.size()) {
+                    const rt_sphere& sp = s->spheres[cl[j]];
+                    make_record(sp.center.x - g[0], sp.center.y - g[1], sp.center.z - g[2], sp.radius * sp.radius, r4);
+                    orig[(size_t)k * K + j] = (uint16_t)cl[j];
+                }
+                float* A = &sfilt[(size_t)k * K * 4 + (size_t)(j / 2) * 8]; int kk = j & 1;
+                A[0 + kk] = r4[0]; A[2 + kk] = r4[1]; A[4 + kk] = r4[2]; A[6 + kk] = r4[3];
+            }
+        }
+    }
+
     TraceParams& tp = h->tp;
     void* d = nullptr;
-    if ((rc = upload_array(h, filt.data(), filt.size() * 4, &d)) != RT_OK) return rc;
-    tp.filt = (const float4*)d;
+    tp.two_level = two_level ? 1u : 0u;
+    tp.n_clusters = n_clusters;
+    if (two_level) {
+        if ((rc = upload_array(h, cfilt.data(), cfilt.size() * 4, &d)) != RT_OK) return rc;
+        tp.filt = (const float4*)d;
+        if ((rc = upload_array(h, sfilt.data(), sfilt.size() * 4, &d)) != RT_OK) return rc;
+        tp.sfilt = (const float4*)d;
+        if ((rc = upload_array(h, orig.data(), orig.size() * 2, &d)) != RT_OK) return rc;
+        tp.orig = (const uint16_t*)d;
+        if ((rc = upload_array(h, cmeta.data(), cmeta.size() * 4, &d)) != RT_OK) return rc;
+        tp.cmeta = (const float*)d;
+        n_pairs = n_cpairs;    // the first-level scan loop runs over the cluster records
+    } else {
+        if ((rc = upload_array(h, filt.data(), filt.size() * 4, &d)) != RT_OK) return rc;
+        tp.filt = (const float4*)d;
+        tp.sfilt = nullptr; tp.orig = nullptr; tp.cmeta = nullptr;
+    }
     if ((rc = upload_array(h, geo.data(), geo.size() * 8, &d)) != RT_OK) return rc;
     tp.geo = (const double4*)d;
     if ((rc = upload_array(h, mat.data(), mat.size() * sizeof(DevMat), &d)) != RT_OK) return rc;
@@ -328,23 +446,29 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         else return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
         h->grid = ctx->sm_count * ctas_per_sm;
     } else {
-        // Candidate configurations: CTA size x {geometry+materials in shared memory or read through L1}. Pick the one
-        // with the most resident threads per SM; ties go to the larger CTA (better class sorting), then to smem scene.
-        // RTB200_WF_BLOCK / RTB200_WF_SCENE_SMEM override the choice (tuning experiments).
-        const char* eb = getenv("RTB200_WF_BLOCK"); const char* es = getenv("RTB200_WF_SCENE_SMEM");
-        int best_threads = -1;
-        for (int blk : {256, 128}) {
-            if (eb && atoi(eb) != blk) continue;
-            for (int in_smem : {1, 0}) {
-                if (es && atoi(es) != in_smem) continue;
-                size_t sm = wavefront_smem_bytes(n, n_pairs, in_smem != 0, blk);
+        // What goes to shared memory besides the first-level filter records and the ray pool, in order of value:
+        // second-level sphere records (two-level mode), exact geometry (read by every f64 confirmation), materials
+        // (read once per hit). Pick the richest set that still leaves kWfThreadsPerSm threads resident per SM.
+        // RTB200_WF_SMEM=<mask> overrides (bit0 sfilt, bit1 geo, bit2 mat) for tuning experiments.
+        const char* es = getenv("RTB200_WF_SMEM");
+        const uint32_t masks[] = {7u, 3u, 1u, 0u};
+        bool found = false;
+        const int want = kWfThreadsPerSm / 256;
+        for (int pass = 0; pass < 2 && !found; ++pass) {
+            for (uint32_t mask : masks) {
+                if (es && (uint32_t)atoi(es) != mask) continue;
+                if (!two_level && (mask & 1u) && mask != 7u) continue;            // bit0 is meaningless without a second level
+                size_t sm = wavefront_smem_bytes(n, n_pairs, n_clusters, two_level, mask, 256);
                 if (sm > ctx->max_smem) continue;
-                int occ = wavefront_max_ctas_per_sm(sm, blk);
-                if (occ * blk > best_threads) { best_threads = occ * blk; h->block = blk; h->smem = sm; tp.scene_in_smem = (uint32_t)in_smem; h->grid = ctx->sm_count * occ; }
+                int occ = wavefront_max_ctas_per_sm(sm, 256);
+                if (occ <= 0) continue;
+                if (pass == 0 && occ < want) continue;                             // first pass: insist on full residency
+                h->block = 256; h->smem = sm; tp.scene_in_smem = mask; h->grid = ctx->sm_count * occ;
+                found = true;
+                break;
             }
         }
-        if (best_threads <= 0)
-            return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
+        if (!found) return fail(RT_ERR_UNSUPPORTED, "first-level filter records exceed shared memory (needs a third level / streaming tiles)");
     }
 
     // ---- per-sample staging: samples per batch bounded by the buffer cap ----
@@ -436,7 +560,7 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         double tr = 0.0;
         for (uint32_t b = 0; b < n_batches; ++b) { CU(cudaEventElapsedTime(&ms, ctx->ev[2 * b], ctx->ev[2 * b + 1])); tr += ms; }
         stats->trace_ms = tr;
-        stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3];
+        stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4];
         if (getenv("RTB200_PRINT_PHASES")) {
             fprintf(stderr, "[rtb200] ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
                     hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);

@@ -14,7 +14,10 @@ constexpr int kCtasPerSm = 2;        // lane-autonomous kernel (rt_trace_kernel)
 #define RT_WF_THREADS 768
 #endif
 constexpr int kWfThreadsPerSm = RT_WF_THREADS;  // CTA-wavefront kernel (rt_wavefront_kernel): resident threads per SM the register budget targets
-constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory
+constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory (lanes kernel)
+constexpr int kClusterK = 4;       // spheres per second-level cluster (slots, padded)
+constexpr int kWfMaxClus = 32;     // wavefront kernel: per-thread list of candidate clusters / first-level candidates
+constexpr int kWfMaxCand = 16;     // wavefront kernel, two-level mode: per-thread list of second-level (sphere) candidates
 
 // 32-byte material record (device copy of the material half of rt_sphere)
 struct DevMat { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };
@@ -38,7 +41,12 @@ struct TraceParams {
     const rtd::DevTex*  tex;       // n_tex
     uint32_t n, n_pairs;
     uint32_t n_lights;
-    uint32_t scene_in_smem;        // 1: geo+mat staged into shared memory as well
+    uint32_t scene_in_smem;        // wavefront kernel: bit0 sfilt, bit1 geo, bit2 mat staged into shared memory; lanes kernel: 0/1 = geo+mat
+    uint32_t two_level;            // 1: `filt` holds CLUSTER bounding-sphere records, `sfilt`/`orig` the member spheres (8 slots per cluster)
+    uint32_t n_clusters;
+    const float4*   sfilt;         // n_clusters*kClusterK float4 (kClusterK/2 pairs per cluster), filter records of the member spheres
+    const uint16_t* orig;          // n_clusters*kClusterK: slot -> sphere index (0xffff = padding)
+    const float*    cmeta;         // n_clusters: |c| of the cluster bound in the recentred frame, rounded up
     double gx, gy, gz;             // recentring offset of the filter frame
     float  er_coef;                // per-ray error coefficient (see DESIGN.md "filter soundness")
     rt_camera cam;
@@ -75,7 +83,7 @@ struct ResolveParams {
 
 size_t trace_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem);
 cudaError_t launch_trace(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st);
-size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem, int block);
+size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t smem_mask, int block);
 cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st);
 int wavefront_max_ctas_per_sm(size_t smem, int block);
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t st);

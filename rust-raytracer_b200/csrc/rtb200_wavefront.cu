@@ -30,7 +30,7 @@ enum : uint32_t { CLS_MISS = 0, CLS_DIFFUSE = 1, CLS_METAL = 2, CLS_GLASS = 3, C
 constexpr uint32_t kDeadLevel = 0xffffffffu;
 
 struct WfSmem {
-    uint32_t filt_off, geo_off, mat_off, cand_off;
+    uint32_t filt_off, sfilt_off, orig_off, cmeta_off, geo_off, mat_off, l1_off, l2_off;
     uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each
     uint32_t bi, work, pix, smp, blk, clo, chi, lvl, shd;   // uint32[kBlock] each
     uint32_t perm;                                  // uint16[kBlock]
@@ -39,13 +39,20 @@ struct WfSmem {
     uint32_t total;
 };
 
-__host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, bool scene_in_smem, uint32_t kBlock) {
+// mask: bit0 second-level sphere records (+slot map), bit1 exact geometry, bit2 materials in shared memory
+__host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t mask, uint32_t kBlock) {
     WfSmem L;
     uint32_t off = 16;   // mbarrier
     L.filt_off = off; off += n_pairs * 32u;
-    L.geo_off = off; if (scene_in_smem) off += n * 32u;
-    L.mat_off = off; if (scene_in_smem) off += n * 32u;
-    L.cand_off = off; off += (uint32_t)kMaxCand * kBlock * 2u;
+    L.sfilt_off = off; if (two_level && (mask & 1u)) off += n_clusters * (uint32_t)(kClusterK * 16);
+    L.orig_off = off; if (two_level && (mask & 1u)) off += n_clusters * (uint32_t)(kClusterK * 2);
+    L.cmeta_off = off; if (two_level && (mask & 1u)) off += n_clusters * 4u;
+    off = (off + 15u) & ~15u;
+    L.geo_off = off; if (mask & 2u) off += n * 32u;
+    L.mat_off = off; if (mask & 4u) off += n * 32u;
+    L.l1_off = off; off += (uint32_t)kWfMaxClus * kBlock * 2u;
+    L.l2_off = off; if (two_level) off += (uint32_t)kWfMaxCand * kBlock * 2u;
+    off = (off + 15u) & ~15u;
     L.ox = off; off += kBlock * 8u; L.oy = off; off += kBlock * 8u; L.oz = off; off += kBlock * 8u;
     L.dx = off; off += kBlock * 8u; L.dy = off; off += kBlock * 8u; L.dz = off; off += kBlock * 8u;
     L.bt = off; off += kBlock * 8u;
@@ -80,17 +87,23 @@ RT_DEV void albedo_of(uint32_t code, const DevMat* mat, float& r, float& g, floa
 
 }  // namespace
 
-size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem, int block) { return wf_layout(n, n_pairs, scene_in_smem, (uint32_t)block).total; }
+size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t smem_mask, int block) {
+    return wf_layout(n, n_pairs, n_clusters, two_level, smem_mask, (uint32_t)block).total;
+}
 
-template <int kBlock, bool EXACT, bool LIGHTS>
+template <int kBlock, bool EXACT, bool LIGHTS, bool TWO>
 __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const WfSmem L = wf_layout(p.n, p.n_pairs, p.scene_in_smem != 0, kBlock);
+    const WfSmem L = wf_layout(p.n, p.n_pairs, p.n_clusters, TWO, p.scene_in_smem, kBlock);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     const float4* s_filt = reinterpret_cast<const float4*>(smem_raw + L.filt_off);
-    uint16_t* s_cand = reinterpret_cast<uint16_t*>(smem_raw + L.cand_off);
-    const double4* geo = p.scene_in_smem ? reinterpret_cast<const double4*>(smem_raw + L.geo_off) : p.geo;
-    const DevMat* mat = p.scene_in_smem ? reinterpret_cast<const DevMat*>(smem_raw + L.mat_off) : p.mat;
+    uint16_t* s_l1 = reinterpret_cast<uint16_t*>(smem_raw + L.l1_off);     // first-level candidates (clusters, or spheres without clustering)
+    uint16_t* s_l2 = reinterpret_cast<uint16_t*>(smem_raw + L.l2_off);     // second-level candidates (spheres), two-level mode
+    const float4* sfilt = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const float4*>(smem_raw + L.sfilt_off) : p.sfilt;
+    const uint16_t* orig = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const uint16_t*>(smem_raw + L.orig_off) : p.orig;
+    const float* cmeta = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const float*>(smem_raw + L.cmeta_off) : p.cmeta;   // |c| of each cluster bound
+    const double4* geo = (p.scene_in_smem & 2u) ? reinterpret_cast<const double4*>(smem_raw + L.geo_off) : p.geo;
+    const DevMat* mat = (p.scene_in_smem & 4u) ? reinterpret_cast<const DevMat*>(smem_raw + L.mat_off) : p.mat;
     double* s_ox = reinterpret_cast<double*>(smem_raw + L.ox); double* s_oy = reinterpret_cast<double*>(smem_raw + L.oy);
     double* s_oz = reinterpret_cast<double*>(smem_raw + L.oz); double* s_dx = reinterpret_cast<double*>(smem_raw + L.dx);
     double* s_dy = reinterpret_cast<double*>(smem_raw + L.dy); double* s_dz = reinterpret_cast<double*>(smem_raw + L.dz);
@@ -117,17 +130,21 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     s_lvl[tid] = kDeadLevel;
     __syncthreads();
     if (tid == 0) {
-        uint32_t bytes = p.n_pairs * 32u + (p.scene_in_smem ? p.n * 64u : 0u);
+        const bool sf = TWO && (p.scene_in_smem & 1u);
+        uint32_t bytes = p.n_pairs * 32u + (sf ? p.n_clusters * (uint32_t)(kClusterK * 18 + 4) : 0u) + ((p.scene_in_smem & 2u) ? p.n * 32u : 0u) + ((p.scene_in_smem & 4u) ? p.n * 32u : 0u);
         mbar_arrive_expect_tx(bar, bytes);
         bulk_stage(smem_raw + L.filt_off, p.filt, p.n_pairs * 32u, bar);
-        if (p.scene_in_smem) {
-            bulk_stage(smem_raw + L.geo_off, p.geo, p.n * 32u, bar);
-            bulk_stage(smem_raw + L.mat_off, p.mat, p.n * 32u, bar);
+        if (sf) {
+            bulk_stage(smem_raw + L.sfilt_off, p.sfilt, p.n_clusters * (uint32_t)(kClusterK * 16), bar);
+            bulk_stage(smem_raw + L.orig_off, p.orig, p.n_clusters * (uint32_t)(kClusterK * 2), bar);
+            bulk_stage(smem_raw + L.cmeta_off, p.cmeta, p.n_clusters * 4u, bar);
         }
+        if (p.scene_in_smem & 2u) bulk_stage(smem_raw + L.geo_off, p.geo, p.n * 32u, bar);
+        if (p.scene_in_smem & 4u) bulk_stage(smem_raw + L.mat_off, p.mat, p.n * 32u, bar);
     }
     mbar_wait(bar, 0);
 
-    unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0;
+    unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0, st_clus = 0;
 #ifdef RT_PROFILE_PHASES
     unsigned long long pf_scan = 0, pf_confirm = 0, pf_waitA = 0, pf_sort = 0, pf_shade = 0, pf_waitC = 0, pf_iters = 0, pf_t = clock64();
 #define PF_MARK(acc) { unsigned long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; }
@@ -182,9 +199,22 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
         uint32_t cls = CLS_DEAD;
         {
             const D3 o = mk(s_ox[tid], s_oy[tid], s_oz[tid]), d = mk(s_dx[tid], s_dy[tid], s_dz[tid]);
-            int nc = 0;
             bool ovf = false;
             const double a = length_squared(d);
+            // exact f64 confirmation. hit_world (raytracer.rs:44-59) keeps the closest root and, on equal t, the first sphere in
+            // list order; because Sphere::hit(t_max) accepts exactly r < t_max with r the first root beyond t_min, that fold equals
+            // the lexicographic minimum of (r, index) over all spheres - so candidates may be confirmed in any order.
+            double best_t = DBL_MAX;
+            int best = -1;
+            auto confirm = [&](int j) {
+                if (j >= (int)p.n) return;   // padding record
+                double4 gq = geo[j];
+                double root;
+                if (sphere_root(mk(gq.x, gq.y, gq.z), gq.w, o, d, a, 0.001, DBL_MAX, root)) {
+                    if (best < 0 || root < best_t || (root == best_t && j < best)) { best_t = root; best = j; }
+                }
+                ++st_cand;
+            };
             if (!EXACT) {
                 // per-ray filter constants in the recentred f32 frame (DESIGN.md "filter soundness")
                 float ofx = __double2float_rn(__dsub_rn(o.x, p.gx)), ofy = __double2float_rn(__dsub_rn(o.y, p.gy)),
@@ -203,59 +233,116 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
                              oz2 = make_float2(2.f * ofz, 2.f * ofz);
                 const float2 nod2 = make_float2(nod, nod);
-                const uint32_t np = p.n_pairs;   // multiple of 4; padding records never hit
-                // candidate column of this thread as a 32-bit shared-memory address; appends are predicated (no branch)
-                const uint32_t c_base = smem_u32(s_cand + tid);
-                const uint32_t c_full = c_base + (uint32_t)(kMaxCand - 8) * kBlock * 2u;
-                uint32_t c_addr = c_base;
-#pragma unroll 2
-                for (uint32_t pp = 0; pp < np; pp += 4) {
-                    float2 Dv[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 A = s_filt[2 * (pp + q)], B = s_filt[2 * (pp + q) + 1];
-                        float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);
-                        float2 bb = __ffma2_rn(cz, dz2, nod2);
-                        float2 tt = __ffma2_rn(cz, oz2, nk);
-                        bb = __ffma2_rn(cy, dy2, bb);
-                        tt = __ffma2_rn(cy, oy2, tt);
-                        bb = __ffma2_rn(cx, dx2, bb);
-                        tt = __ffma2_rn(cx, ox2, tt);
-                        Dv[q] = __ffma2_rn(bb, bb, tt);
-                    }
-                    float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
-                    if (m >= thr) {   // rare: some lane has a candidate among these 8 spheres; appends in ascending index order
-                        if (c_addr > c_full) { ovf = true; }
-                        else {
+                const uint32_t np = p.n_pairs;   // multiple of 8; padding records never hit
+                // Per-thread candidate lists live in shared memory as columns (entry k of thread t at [k*kBlock + t]); appends are
+                // predicated stores through a 32-bit shared address. A list that is about to fill up is drained on the spot, so
+                // no ray ever falls back to brute force because of list capacity.
+                const uint32_t l1_base = smem_u32(s_l1 + tid);
+                const uint32_t l1_full = l1_base + (uint32_t)(kWfMaxClus - 8) * kBlock * 2u;
+                uint32_t l1_addr = l1_base;
+                const uint32_t l2_base = smem_u32(s_l2 + tid);
+                const uint32_t l2_full = l2_base + (uint32_t)(kWfMaxCand - kClusterK) * kBlock * 2u;
+                uint32_t l2_addr = l2_base;
+#define RT_FILTER_PAIRS(REC, DV, NP)                                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < (NP); ++q) {                                                                              \
+        float4 A = (REC)[2 * q], B = (REC)[2 * q + 1];                                                                               \
+        float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);       \
+        float2 bb = __ffma2_rn(cz, dz2, nod2);                                                                                       \
+        float2 tt = __ffma2_rn(cz, oz2, nk);                                                                                         \
+        bb = __ffma2_rn(cy, dy2, bb);                                                                                                \
+        tt = __ffma2_rn(cy, oy2, tt);                                                                                                \
+        bb = __ffma2_rn(cx, dx2, bb);                                                                                                \
+        tt = __ffma2_rn(cx, ox2, tt);                                                                                                \
+        (DV)[q] = __ffma2_rn(bb, bb, tt);                                                                                            \
+    }
+#define RT_APPEND_IF(ADDR, VAL, ID)                                                                                                   \
+    asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}" \
+                 : "+r"(ADDR) : "f"(VAL), "f"(thr), "r"(ID), "n"(kBlock * 2) : "memory")
+                // Loop structure: each level fills its list until it is nearly full (or its input ends), the next level drains
+                // it, and the outer loop resumes. Every drain therefore exists exactly once in the code (small I-cache footprint)
+                // and no ray ever falls back to brute force because of list capacity.
+                uint32_t pp = 0;
+                for (;;) {
+                    // ---- level 1: records of `filt` (cluster bounds, or the spheres themselves without clustering) ----
+#pragma unroll 1
+                    for (; pp < np && l1_addr <= l1_full; pp += 4) {
+                        float2 Dv[4];
+                        const float4* rec = s_filt + 2 * pp;
+                        RT_FILTER_PAIRS(rec, Dv, 4)
+                        float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
+                        if (m >= thr) {   // rare: some lane has a candidate among these 8 records
                             const uint32_t j0 = 2u * pp;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}"
-                                             : "+r"(c_addr) : "f"(Dv[q].x), "f"(thr), "r"(j0 + 2u * q), "n"(kBlock * 2) : "memory");
-                                asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}"
-                                             : "+r"(c_addr) : "f"(Dv[q].y), "f"(thr), "r"(j0 + 2u * q + 1u), "n"(kBlock * 2) : "memory");
+                                RT_APPEND_IF(l1_addr, Dv[q].x, j0 + 2u * q);
+                                RT_APPEND_IF(l1_addr, Dv[q].y, j0 + 2u * q + 1u);
                             }
                         }
                     }
+                    if (TWO) {
+                        // ---- level 2: the kClusterK member spheres of every listed cluster (per-thread addresses) ----
+                        const int n1 = (int)((l1_addr - l1_base) / (kBlock * 2u));
+                        const float beta_o = 16.0f * 5.9604645e-8f * sqrtf(oo);      // rounding bound of b = (c-o).d on the ray's side
+                        int k = 0;
+                        for (;;) {
+#pragma unroll 1
+                            for (; k < n1 && l2_addr <= l2_full; ++k) {
+                                const uint32_t cb = s_l1[k * kBlock + tid];
+                                if (cb >= p.n_clusters) continue;                   // padding record
+                                // Behind-the-origin cull: with b = (c-o).d^ and q = |c-o|^2 - R^2, b < 0 and q > 0 put both roots of
+                                // the bounding sphere at negative t, hence every member root too. Both signs are required beyond
+                                // their rounding margins, otherwise the cluster is processed.
+                                const uint32_t pr = cb >> 1, hi = cb & 1u;
+                                const float4 CA = s_filt[2 * pr], CB = s_filt[2 * pr + 1];
+                                const float ccx = hi ? CA.y : CA.x, ccy = hi ? CA.w : CA.z, ccz = hi ? CB.y : CB.x, cnk = hi ? CB.w : CB.z;
+                                const float cbb = fmaf(ccx, dnx, fmaf(ccy, dny, fmaf(ccz, dnz, nod)));
+                                const float ctt = fmaf(ccx, 2.f * ofx, fmaf(ccy, 2.f * ofy, fmaf(ccz, 2.f * ofz, cnk)));
+                                const float cD = fmaf(cbb, cbb, ctt);               // ~ b^2 - q + Es + |o|^2
+                                const float cabs = cmeta[cb];                       // |c| of the bound (f32, rounded up)
+                                const float qlow = fmaf(cbb, cbb, oo) - cD;         // ~ q - Es  (<= q up to rounding)
+                                const float eq = 2.0e-5f * fmaf(cabs, cabs, oo);    // >= 3x the rounding bound 96u(|c|^2+|o|^2)
+                                if (cbb < -(16.0f * 5.9604645e-8f * cabs + beta_o) * 1.5f - 1e-30f && qlow > eq) continue;
+                                float2 Dv[kClusterK / 2];
+                                const float4* rec = sfilt + (uint32_t)kClusterK * cb;
+                                RT_FILTER_PAIRS(rec, Dv, kClusterK / 2)
+                                float m = fmaxf(Dv[0].x, Dv[0].y);
+#pragma unroll
+                                for (int q = 1; q < kClusterK / 2; ++q) m = fmaxf(m, fmaxf(Dv[q].x, Dv[q].y));
+                                if (m >= thr) {
+                                    const uint16_t* og = orig + (uint32_t)kClusterK * cb;
+#pragma unroll
+                                    for (int q = 0; q < kClusterK / 2; ++q) {
+                                        const uint32_t w = *reinterpret_cast<const uint32_t*>(og + 2 * q);   // 2 x u16 slot -> sphere index
+                                        RT_APPEND_IF(l2_addr, Dv[q].x, w & 0xffffu);
+                                        RT_APPEND_IF(l2_addr, Dv[q].y, w >> 16);
+                                    }
+                                }
+                                ++st_clus;
+                            }
+                            // ---- exact f64 confirmation of the listed spheres ----
+                            const int n2 = (int)((l2_addr - l2_base) / (kBlock * 2u));
+                            for (int j = 0; j < n2; ++j) confirm((int)s_l2[j * kBlock + tid]);
+                            l2_addr = l2_base;
+                            if (k >= n1) break;
+                        }
+                        l1_addr = l1_base;
+                    } else {
+                        const int n1 = (int)((l1_addr - l1_base) / (kBlock * 2u));
+                        for (int j = 0; j < n1; ++j) confirm((int)s_l1[j * kBlock + tid]);
+                        l1_addr = l1_base;
+                    }
+                    if (pp >= np) break;
                 }
-                nc = (int)((c_addr - c_base) / (kBlock * 2u));
+                PF_MARK(pf_scan)
+#undef RT_FILTER_PAIRS
+#undef RT_APPEND_IF
             } else {
                 ovf = alive;
             }
-            PF_MARK(pf_scan)
-            // exact f64 confirmation, ascending sphere index => first index wins ties like raytracer.rs:52-56
             if (alive) {
-                double best_t = DBL_MAX;
-                int best = -1;
-                const int cnt_c = ovf ? (int)p.n : nc;
-                if (ovf) ++st_ovf;
-                st_cand += (unsigned)cnt_c;
-                for (int k = 0; k < cnt_c; ++k) {
-                    int j = ovf ? k : (int)s_cand[k * kBlock + tid];
-                    if (j >= (int)p.n) continue;   // padding record
-                    double4 gq = geo[j];
-                    double root;
-                    if (sphere_root(mk(gq.x, gq.y, gq.z), gq.w, o, d, a, 0.001, best_t, root)) { best_t = root; best = j; }
+                if (ovf) {   // EXACT variant, or a ray outside the f32 filter's safe range: every sphere in f64
+                    ++st_ovf;
+                    for (int k = 0; k < (int)p.n; ++k) confirm(k);
                 }
                 s_bt[tid] = best_t;
                 s_bi[tid] = (uint32_t)best;
@@ -267,8 +354,8 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 ++st_rays;
             }
         }
-
         PF_MARK(pf_confirm)
+
         // =========================== sort: compact the live slots class by class ===========================
         uint32_t wbase = 0, rank = 0;
 #pragma unroll
@@ -481,8 +568,10 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
         st_cand += __shfl_down_sync(FULL, st_cand, off);
         st_ovf += __shfl_down_sync(FULL, st_ovf, off);
         st_samples += __shfl_down_sync(FULL, st_samples, off);
+        st_clus += __shfl_down_sync(FULL, st_clus, off);
     }
     if (lane == 0) {
+        atomicAdd(&p.stat[4], st_clus);
         atomicAdd(&p.stat[0], st_rays);
         atomicAdd(&p.stat[1], st_cand);
         atomicAdd(&p.stat[2], st_ovf);
@@ -490,31 +579,29 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     }
 }
 
-template <int B, bool E, bool LI>
+template <int B, bool E, bool LI, bool TW>
 static cudaError_t launch_wf(const TraceParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E, LI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E, LI, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rt_wavefront_kernel<B, E, LI><<<grid, B, smem, st>>>(p);
+    rt_wavefront_kernel<B, E, LI, TW><<<grid, B, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st) {
-    const bool li = p.n_lights > 0;
-    if (block == 128) return exact ? launch_wf<128, true, false>(p, grid, smem, st) : launch_wf<128, false, false>(p, grid, smem, st);
-    if (li) return exact ? launch_wf<256, true, true>(p, grid, smem, st) : launch_wf<256, false, true>(p, grid, smem, st);
-    return exact ? launch_wf<256, true, false>(p, grid, smem, st) : launch_wf<256, false, false>(p, grid, smem, st);
+    (void)block;
+    const bool li = p.n_lights > 0, tw = p.two_level != 0;
+    if (exact) {   // every sphere in f64: the filter levels are not used at all
+        return li ? launch_wf<256, true, true, false>(p, grid, smem, st) : launch_wf<256, true, false, false>(p, grid, smem, st);
+    }
+    if (tw) return li ? launch_wf<256, false, true, true>(p, grid, smem, st) : launch_wf<256, false, false, true>(p, grid, smem, st);
+    return li ? launch_wf<256, false, true, false>(p, grid, smem, st) : launch_wf<256, false, false, false>(p, grid, smem, st);
 }
 
 int wavefront_max_ctas_per_sm(size_t smem, int block) {
+    (void)block;
     int nb = 0;
-    cudaError_t e;
-    if (block == 128) {
-        cudaFuncSetAttribute(rt_wavefront_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<128, false, false>, 128, smem);
-    } else {
-        cudaFuncSetAttribute(rt_wavefront_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false, true>, 256, smem);
-    }
+    cudaFuncSetAttribute(rt_wavefront_kernel<256, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false, true, true>, 256, smem);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
 }

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(os.path.dirname(_HERE), 
 
 RT_LAMBERTIAN, RT_METAL, RT_GLASS, RT_TEXTURE, RT_LIGHT = 0, 1, 2, 3, 4
 RT_SKY_NONE, RT_SKY_GRADIENT, RT_SKY_TEXTURE = 0, 1, 2
-RT_VARIANT_AUTO, RT_VARIANT_FILTERED, RT_VARIANT_EXACT_F64, RT_VARIANT_LANES = 0, 1, 2, 3
+RT_VARIANT_AUTO, RT_VARIANT_FILTERED, RT_VARIANT_EXACT_F64, RT_VARIANT_LANES, RT_VARIANT_BRUTE_FORCE = 0, 1, 2, 3, 4
 
 DEFAULT_SEED = 0x5EED
 
@@ -78,7 +78,7 @@ class rt_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("candidates", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("wall_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("batches", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("clusters", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -106,11 +106,11 @@ def test_gpu_matches_committed_golden(name, mk):
     assert np.array_equal(lin, g["linear"]) and np.array_equal(img, g["rgb8"]) and st["rays"] == int(g["rays"])
 
 
-@pytest.mark.parametrize("variant", [R.RT_VARIANT_FILTERED, R.RT_VARIANT_EXACT_F64, R.RT_VARIANT_LANES])
+@pytest.mark.parametrize("variant", [R.RT_VARIANT_FILTERED, R.RT_VARIANT_EXACT_F64, R.RT_VARIANT_LANES, R.RT_VARIANT_BRUTE_FORCE])
 def test_cover_scene_bit_exact(variant):
     st = _exact(scenes.cover_scene(200, 150, 8), R.make_options(variant=variant))
     if variant != R.RT_VARIANT_EXACT_F64:
-        assert st["candidates"] / st["rays"] < 8.0     # the f32 filter prunes >98 % of the 484 sphere tests
+        assert st["candidates"] / st["rays"] < 8.0     # the f32 filter levels prune >98 % of the 484 sphere tests
     else:
         assert st["candidates"] == st["rays"] * 484
 
@@ -119,6 +119,7 @@ def test_cover_scene_bit_exact(variant):
 def test_mixed_materials_bit_exact(seed):
     _exact(R.Scene.from_config(mixed_config(96, 72, 4, 20, seed=seed)))
     _exact(R.Scene.from_config(mixed_config(96, 72, 4, 20, seed=seed)), R.make_options(variant=R.RT_VARIANT_LANES))
+    _exact(R.Scene.from_config(mixed_config(96, 72, 4, 20, seed=seed)), R.make_options(variant=R.RT_VARIANT_BRUTE_FORCE))
 
 
 @pytest.mark.parametrize("offset", [(1.0e3, 50.0, -2.0e3), (1.0e5, 0.0, 1.0e5), (-3.0e6, 1.0e3, 7.0e6)])
@@ -126,6 +127,7 @@ def test_filter_is_sound_far_from_the_origin(offset):
     """The f32 filter must never drop a sphere the f64 test accepts, however large the coordinates."""
     sc = R.Scene.from_config(mixed_config(64, 48, 3, 12, seed=4, offset=offset))
     _exact(sc, R.make_options(variant=R.RT_VARIANT_FILTERED))
+    _exact(sc, R.make_options(variant=R.RT_VARIANT_BRUTE_FORCE))
 
 
 def test_black_sky_and_depth_edges():

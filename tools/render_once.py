@@ -18,4 +18,4 @@ rs = R.ResidentScene(sc, R.make_options(variant=variant))
 out = torch.empty(sc.c.height * sc.c.width * 3, dtype=torch.uint8, device='cuda')
 for i in range(reps):
     st = rs.render(out.data_ptr())
-    print(f"{name}: rays={st['rays']} device_ms={st['device_ms']:.3f} trace_ms={st['trace_ms']:.3f} Mrays/s={st['rays']/st['device_ms']/1e3:.1f} cand/ray={st['candidates']/max(st['rays'],1):.2f}", flush=True)
+    print(f"{name}: rays={st['rays']} device_ms={st['device_ms']:.3f} trace_ms={st['trace_ms']:.3f} Mrays/s={st['rays']/st['device_ms']/1e3:.1f} cand/ray={st['candidates']/max(st['rays'],1):.2f} clusters/ray={st['clusters']/max(st['rays'],1):.2f}", flush=True)
