@@ -562,8 +562,8 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         stats->trace_ms = tr;
         stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4];
         if (getenv("RTB200_PRINT_PHASES")) {
-            fprintf(stderr, "[rtb200] ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
-                    hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
+            fprintf(stderr, "[rtb200] stage_mismatch=%llu ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
+                    hstat[6], hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
         }
         if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
         if (tp.max_depth == 0) stats->samples = (uint64_t)tp.npix_local * spp;   // no kernel ran: every sample is black

@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm) rt_trace_kernel(const __gr
             float dnx = dfx * inv, dny = dfy * inv, dnz = dfz * inv;
             float nod = -fmaf(ofx, dnx, fmaf(ofy, dny, ofz * dnz));
             float thr = __fmul_rd(oo, p.er_coef);
-            if (!alive) thr = __int_as_float(0x7f800000);   // +inf: dead lanes never produce candidates
-            if (alive && !ok) { ovf = true; thr = __int_as_float(0x7f800000); }
+            if (!alive) thr = __int_as_float(0x7fc00000);   // NaN: every comparison is false for dead lanes
+            if (alive && !ok) { ovf = true; thr = __int_as_float(0x7fc00000); }
             const float2 dx2 = make_float2(dnx, dnx), dy2 = make_float2(dny, dny), dz2 = make_float2(dnz, dnz);
             const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
                          oz2 = make_float2(2.f * ofz, 2.f * ofz);

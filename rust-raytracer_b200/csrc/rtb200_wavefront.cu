@@ -143,6 +143,15 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
         if (p.scene_in_smem & 4u) bulk_stage(smem_raw + L.mat_off, p.mat, p.n * 32u, bar);
     }
     mbar_wait(bar, 0);
+#ifdef RT_DEBUG_STAGE
+    {   // verify the TMA staging of the first-level records against global memory
+        unsigned long long bad = 0;
+        const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(p.filt);
+        const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(smem_raw + L.filt_off);
+        for (uint32_t i = tid; i < p.n_pairs * 8u; i += kBlock) if (gsrc[i] != ssrc[i]) ++bad;
+        if (bad) atomicAdd(&p.stat[6], bad);
+    }
+#endif
 
     unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0, st_clus = 0;
 #ifdef RT_PROFILE_PHASES
@@ -227,8 +236,8 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 float dnx = dfx * inv, dny = dfy * inv, dnz = dfz * inv;
                 float nod = -fmaf(ofx, dnx, fmaf(ofy, dny, ofz * dnz));
                 float thr = __fmul_rd(oo, p.er_coef);
-                if (!alive) thr = __int_as_float(0x7f800000);   // +inf: empty slots never produce candidates
-                if (alive && !ok) { ovf = true; thr = __int_as_float(0x7f800000); }
+                if (!alive) thr = __int_as_float(0x7fc00000);   // NaN: every comparison is false, so empty slots (whose o,d are garbage, possibly +-inf) never produce candidates
+                if (alive && !ok) { ovf = true; thr = __int_as_float(0x7fc00000); }
                 const float2 dx2 = make_float2(dnx, dnx), dy2 = make_float2(dny, dny), dz2 = make_float2(dnz, dnz);
                 const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
                              oz2 = make_float2(2.f * ofz, 2.f * ofz);

@@ -270,3 +270,32 @@ def test_too_many_lights_is_refused():
     with pytest.raises(R.RtError) as e:
         R.render_rgb8(R.Scene.from_config(cfg))
     assert e.value.code == -4
+
+
+# ---- N4: two-level culling on the large config ---------------------------------------------------------------
+def test_rtiow_10k_spheres_bit_exact():
+    """BASELINE config C4's scene (seeded restatement of config.rs:149-226 on a 100x100 grid, 10,000 spheres) at a
+    size the oracle finishes in seconds. The second-level sphere records (160 KB) do not fit shared memory next to
+    the ray pool, so this also covers the global-memory path of the second level."""
+    cfg = scenes._variant(scenes.rtiow_config(50), 128, 72, 3, 50)
+    sc = R.Scene.from_config(cfg)
+    st = _exact(sc)
+    assert sc.n_spheres > 9900 and st["candidates"] / st["rays"] < 8.0 and 0 < st["clusters"] / st["rays"] < 64.0
+    _exact(sc, R.make_options(variant=R.RT_VARIANT_BRUTE_FORCE))
+
+
+def test_two_level_equals_brute_force_on_awkward_cluster_shapes():
+    """Clusters with 1..4 members, several radius classes, coincident spheres, zero and negative radii."""
+    rng = np.random.default_rng(7)
+    objs = []
+    for i in range(75):
+        r = float(rng.choice([0.05, 0.11, 0.3, 0.31, 0.9, 2.5])) * (-1.0 if i % 11 == 0 else 1.0)
+        m = [{"Lambertian": {"albedo": [0.7, 0.6, 0.5]}}, {"Metal": {"albedo": [0.9, 0.9, 0.9], "fuzz": 0.05}}, {"Glass": {"index_of_refraction": 1.5}}][i % 3]
+        objs.append({"center": _v(*rng.uniform(-5, 5, 3)), "radius": r, "material": m})
+    objs.append({"center": _v(0, 0, 0), "radius": 0.0, "material": {"Lambertian": {"albedo": [1, 0, 0]}}})
+    objs += [dict(objs[5]), dict(objs[5])]   # three coincident copies: the first index must win
+    sc = R.Scene.from_config(base_config(72, 54, 3, 10, objs, look_from=(9, 3, 7), look_at=(0, 0, 0), vfov=50.0))
+    a, sa = R.render_linear(sc)
+    b, sb = R.render_linear(sc, R.make_options(variant=R.RT_VARIANT_BRUTE_FORCE))
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"] and sa["clusters"] > 0 and sb["clusters"] == 0
+    _exact(sc)
