@@ -114,6 +114,7 @@ typedef struct {
     uint32_t batches;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t clusters;      /* second-level blocks visited (two-level culling; diagnostic) */
+    uint64_t frames;        /* frames covered by device_ms / trace_ms / kernel_launches (1 for the blocking calls) */
 } rt_stats;
 
 enum rt_status {
@@ -148,8 +149,13 @@ int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, floa
 /* Resident form (scene stays in HBM between frames; output stays on the device). */
 typedef struct rtb200_scene_t* rtb200_scene_handle;
 int rtb200_scene_upload(const rt_scene* scene, const rt_options* opts, rtb200_scene_handle* out);
-/* dev_rgb8 / dev_linear_f32 are DEVICE pointers (either may be NULL); stream is a cudaStream_t or NULL. */
+/* dev_rgb8 / dev_linear_f32 are DEVICE pointers (either may be NULL); stream is a cudaStream_t, or NULL for the library's
+ * own non-blocking stream (pass cudaStreamLegacy / cudaStreamPerThread explicitly to order against the default stream). */
 int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream, rt_stats* stats);
+/* Non-blocking form for frame loops: enqueue a frame on `stream` and return; rtb200_render_device_wait() blocks until the
+ * most recently enqueued frame of the handle is done and returns its statistics. Work of successive frames is ordered by the stream. */
+int rtb200_render_device_async(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream);
+int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats);
 int rtb200_scene_release(rtb200_scene_handle h);
 
 /* load_texture_image — materials.rs:213-219, config.rs:36-47: decode a baseline JPEG file to RGB8 (host-side scene staging

@@ -120,6 +120,9 @@ struct rtb200_scene_t {
     size_t smem = 0;
     uint32_t spp_batch = 0;
     std::vector<void*> owned;   // device allocations owned by the handle
+    cudaStream_t last_stream = nullptr;   // stream, batch and launch count of the most recently enqueued frame
+    uint32_t last_batches = 0, last_launches = 0;
+    uint32_t pending_frames = 0;          // frames enqueued since the last wait (their events sit in the context's event ring)
     uint64_t h2d_bytes = 0;
 };
 
@@ -485,14 +488,14 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     return RT_OK;
 }
 
-int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, rt_stats* stats) {
+// Enqueue one frame on `stream_in` (or the context's stream) without waiting for it.
+static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in) {
     if (!h) return fail(RT_ERR_INVALID, "null scene handle");
-    auto wall0 = std::chrono::steady_clock::now();
     DeviceCtx* ctx = h->ctx;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream_in ? (cudaStream_t)stream_in : ctx->stream;
     TraceParams tp = h->tp;
-    if (stats) memset(stats, 0, sizeof *stats);
+    h->last_stream = st; h->last_batches = 0; h->last_launches = 0;
     if (tp.npix_local == 0) return RT_OK;
 
     const uint32_t spp = tp.spp, spb = h->spp_batch;
@@ -514,9 +517,13 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
     }
     tp.frames = (ShadowFrame*)ctx->frames.p;
     tp.lterm = (float*)ctx->lterm.p;
-    while (ctx->ev.size() < 2 * (size_t)n_batches) {
+    // event ring: every pending frame owns 2 + 2*n_batches events (begin, end, and a pair around each trace launch)
+    const uint32_t kRing = 64, per_frame = 2 + 2 * n_batches;
+    if (h->pending_frames >= kRing) return fail(RT_ERR_INVALID, "more than 64 frames enqueued without rtb200_render_device_wait");
+    while (ctx->ev.size() < (size_t)kRing * per_frame) {
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
+    cudaEvent_t* fev = ctx->ev.data() + (size_t)h->pending_frames * per_frame;
     unsigned long long* stat = (unsigned long long*)ctx->small.p;
     unsigned int* counters = (unsigned int*)((char*)ctx->small.p + 256);
     CU(cudaMemsetAsync(ctx->small.p, 0, 256 + (size_t)n_batches * 4, st));
@@ -526,14 +533,14 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
     tp.stack_stride = threads_total;
     tp.stat = stat;
 
-    CU(cudaEventRecord(ctx->ev_begin, st));
+    CU(cudaEventRecord(fev[0], st));
     uint32_t launches = 0;
     for (uint32_t b = 0; b < n_batches; ++b) {
         tp.s0 = b * spb;
         tp.s_count = std::min(spb, spp - tp.s0);
         tp.total_work = tp.s_count * tp.npix_local;
         tp.work_counter = counters + b;
-        CU(cudaEventRecord(ctx->ev[2 * b], st));
+        CU(cudaEventRecord(fev[2 + 2 * b], st));
         if (tp.max_depth == 0) {
             CU(cudaMemsetAsync(tp.samplebuf, 0, (size_t)tp.total_work * 16, st));   // ray_color(depth 0) = black, no ray (raytracer.rs:80-82)
         } else if (h->lanes) {
@@ -541,7 +548,7 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         } else {
             CU(launch_wavefront(tp, h->grid, h->smem, h->block, h->exact, st));
         }
-        CU(cudaEventRecord(ctx->ev[2 * b + 1], st));
+        CU(cudaEventRecord(fev[3 + 2 * b], st));
         ResolveParams q{};
         q.samplebuf = tp.samplebuf; q.accum = (float*)ctx->accum.p; q.npix_local = tp.npix_local; q.s_count = tp.s_count;
         q.first = b == 0; q.last = b + 1 == n_batches; q.spp = spp;
@@ -549,29 +556,61 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
         CU(launch_resolve(q, st));
         launches += 2;
     }
-    CU(cudaEventRecord(ctx->ev_end, st));
+    CU(cudaEventRecord(fev[1], st));
+    h->last_batches = n_batches; h->last_launches = launches;
+    ++h->pending_frames;
+    return RT_OK;
+}
+
+// Wait for the most recently enqueued frame of `h` and fetch its statistics.
+static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
+    if (!h) return fail(RT_ERR_INVALID, "null scene handle");
+    DeviceCtx* ctx = h->ctx;
+    CU(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (h->tp.npix_local == 0 || h->last_batches == 0 || h->pending_frames == 0) return RT_OK;
+    cudaStream_t st = h->last_stream;
     unsigned long long hstat[16] = {0};
-    CU(cudaMemcpyAsync(hstat, stat, sizeof hstat, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hstat, ctx->small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
     if (stats) {
+        // device_ms / trace_ms: summed over every frame enqueued since the previous wait; the counters are the last frame's
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-        stats->device_ms = ms;
-        double tr = 0.0;
-        for (uint32_t b = 0; b < n_batches; ++b) { CU(cudaEventElapsedTime(&ms, ctx->ev[2 * b], ctx->ev[2 * b + 1])); tr += ms; }
-        stats->trace_ms = tr;
+        double dv = 0.0, tr = 0.0;
+        const uint32_t per_frame = 2 + 2 * h->last_batches;
+        for (uint32_t f = 0; f < h->pending_frames; ++f) {
+            cudaEvent_t* fev = ctx->ev.data() + (size_t)f * per_frame;
+            CU(cudaEventElapsedTime(&ms, fev[0], fev[1])); dv += ms;
+            for (uint32_t b = 0; b < h->last_batches; ++b) { CU(cudaEventElapsedTime(&ms, fev[2 + 2 * b], fev[3 + 2 * b])); tr += ms; }
+        }
+        stats->device_ms = dv; stats->trace_ms = tr; stats->frames = h->pending_frames;
         stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4];
         if (getenv("RTB200_PRINT_PHASES")) {
             fprintf(stderr, "[rtb200] stage_mismatch=%llu ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
                     hstat[6], hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
         }
-        if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
-        if (tp.max_depth == 0) stats->samples = (uint64_t)tp.npix_local * spp;   // no kernel ran: every sample is black
-        stats->kernel_launches = launches; stats->batches = n_batches;
-        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        if (h->tp.max_depth == 0) stats->samples = (uint64_t)h->tp.npix_local * h->tp.spp;   // no kernel ran: every sample is black
+        stats->kernel_launches = h->last_launches * h->pending_frames; stats->batches = h->last_batches;
     }
+    h->pending_frames = 0;
     return RT_OK;
 }
+
+int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, rt_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    int rc = render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in);
+    if (rc != RT_OK) return rc;
+    rc = render_collect(h, stats);
+    if (rc == RT_OK && stats) stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return rc;
+}
+
+int rtb200_render_device_async(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in) {
+    return render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in);
+}
+
+int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats) { return render_collect(h, stats); }
 
 static int render_host(const rt_scene* s, const rt_options* opts, uint8_t* out_rgb8, float* out_lin, rt_stats* stats) {
     auto wall0 = std::chrono::steady_clock::now();

@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 }
                 ++st_cand;
             };
-            if (!EXACT) {
+            const bool warp_has_ray = __ballot_sync(FULL, alive) != 0u;   // a warp whose 32 slots are all empty skips the scan (frame tail)
+            if (!EXACT && warp_has_ray) {
                 // per-ray filter constants in the recentred f32 frame (DESIGN.md "filter soundness")
                 float ofx = __double2float_rn(__dsub_rn(o.x, p.gx)), ofy = __double2float_rn(__dsub_rn(o.y, p.gy)),
                       ofz = __double2float_rn(__dsub_rn(o.z, p.gz));
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 PF_MARK(pf_scan)
 #undef RT_FILTER_PAIRS
 #undef RT_APPEND_IF
-            } else {
+            } else if (EXACT) {
                 ovf = alive;
             }
             if (alive) {

@@ -78,7 +78,7 @@ class rt_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("candidates", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("wall_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("batches", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("clusters", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("clusters", C.c_uint64), ("frames", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "rtb200_render_rgb8", "rtb200_render_linear_f32", "rtb200_scene_upload", "rtb200_render_device",
     "rtb200_scene_release", "rtb200_probe_sphere_hit", "rtb200_probe_refract", "rtb200_probe_reflectance",
     "rtb200_probe_sky", "rtb200_probe_get_ray", "rtb200_probe_rng", "rtb200_probe_quantise",
-    "rtb200_decode_jpeg_file", "rtb200_free",
+    "rtb200_decode_jpeg_file", "rtb200_free", "rtb200_render_device_async", "rtb200_render_device_wait",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.rtb200_scene_upload.argtypes = [C.POINTER(rt_scene), C.POINTER(rt_options), C.POINTER(C.c_void_p)]
     L.rtb200_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]
     L.rtb200_scene_release.argtypes = [C.c_void_p]
+    L.rtb200_render_device_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.rtb200_render_device_wait.argtypes = [C.c_void_p, C.POINTER(rt_stats)]
     L.rtb200_probe_sphere_hit.argtypes = [C.POINTER(rt_vec3), C.c_double, C.POINTER(rt_vec3), C.POINTER(rt_vec3), C.c_double,
                                           C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(rt_vec3),
                                           C.POINTER(rt_vec3), C.POINTER(C.c_int32)]
@@ -338,6 +340,15 @@ class ResidentScene:
         st = rt_stats()
         _check(lib().rtb200_render_device(self.h, C.c_void_p(dev_rgb8_ptr or None), C.c_void_p(dev_linear_ptr or None),
                                           C.c_void_p(stream or None), C.byref(st)))
+        return st.as_dict()
+
+    def render_async(self, dev_rgb8_ptr: int = 0, dev_linear_ptr: int = 0, stream: int = 0):
+        """Enqueue a frame without waiting (frame loops); pair with :meth:`wait`."""
+        _check(lib().rtb200_render_device_async(self.h, C.c_void_p(dev_rgb8_ptr or None), C.c_void_p(dev_linear_ptr or None), C.c_void_p(stream or None)))
+
+    def wait(self) -> dict:
+        st = rt_stats()
+        _check(lib().rtb200_render_device_wait(self.h, C.byref(st)))
         return st.as_dict()
 
     def release(self):

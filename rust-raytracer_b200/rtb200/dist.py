@@ -16,6 +16,12 @@ import torch.distributed as dist
 
 from . import ResidentScene, Scene, make_options, shard_row_indices, shard_rows
 
+CUDA_STREAM_LEGACY = 0x1   # cudaStreamLegacy: torch's default stream has handle 0, which the C ABI reads as "use the library's own stream"
+
+
+def _torch_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
+
 
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -86,12 +92,23 @@ class DistributedRenderer:
 
     def render(self) -> dict:
         """One frame on the current torch stream. Returns this rank's stats; rank 0's `frame` holds the image."""
-        st = self.resident.render(self.shard.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        st = self.resident.render(self.shard.data_ptr(), 0, _torch_stream())
         if self.world > 1:
             gather_frame(self.shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
         else:
             self.frame = self.shard[: self.h]
         return st
+
+    def render_async(self):
+        """Enqueue one frame (trace + resolve + gather) on the current torch stream without waiting; wait() collects stats."""
+        self.resident.render_async(self.shard.data_ptr(), 0, _torch_stream())
+        if self.world > 1:
+            gather_frame(self.shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
+        else:
+            self.frame = self.shard[: self.h]
+
+    def wait(self) -> dict:
+        return self.resident.wait()
 
     def release(self):
         self.resident.release()

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(R.rt_vec3) == 24 and C.sizeof(R.rt_camera) == 96 and C.sizeof(R.rt_sphere) == 64
     assert C.sizeof(R.rt_image) == 24 and C.sizeof(R.rt_sky) == 32
     assert C.sizeof(R.rt_scene) == 16 + 96 + 32 + 16 + 16 + 8
-    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 80
+    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 88
 
 
 @pytest.mark.parametrize("args", [
