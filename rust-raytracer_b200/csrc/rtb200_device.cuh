@@ -79,6 +79,36 @@ RT_DEV double rng_m1_1(Rng& g, uint32_t k0, uint32_t k1) {
     double v01 = __dsub_rn(__longlong_as_double((long long)bits), 1.0);
     return __dadd_rn(__dmul_rn(v01, 2.0), -1.0);
 }
+// Same stream, same draws, but two rejection trials per loop trip and their three Philox blocks computed together
+// (instruction-level parallelism: the shade stage is bound by the latency of this dependent chain, not by throughput).
+RT_DEV double u64_to_m1_1(uint32_t lo, uint32_t hi) {
+    unsigned long long bits = ((((unsigned long long)hi << 32) | lo) >> 12) | 0x3FF0000000000000ull;
+    double v01 = __dsub_rn(__longlong_as_double((long long)bits), 1.0);
+    return __dadd_rn(__dmul_rn(v01, 2.0), -1.0);
+}
+RT_DEV D3 random_in_unit_sphere_ilp(Rng& g, uint32_t k0, uint32_t k1) {                                       // point3d.rs:22-38
+    for (;;) {
+        uint32_t A[4], B[4], Cc[4];
+        philox4x32_10(g.blk, g.sample, g.pixel, 0u, k0, k1, A);
+        philox4x32_10(g.blk + 1u, g.sample, g.pixel, 0u, k0, k1, B);
+        philox4x32_10(g.blk + 2u, g.sample, g.pixel, 0u, k0, k1, Cc);
+        // u[i] = the next unread u64 draws of the stream: (cached,) A.lo, A.hi, B.lo, B.hi, C.lo, C.hi
+        uint32_t lo[7], hi[7];
+        if (g.has) { lo[0] = g.c_lo; hi[0] = g.c_hi; lo[1] = A[0]; hi[1] = A[1]; lo[2] = A[2]; hi[2] = A[3]; lo[3] = B[0]; hi[3] = B[1]; lo[4] = B[2]; hi[4] = B[3]; lo[5] = Cc[0]; hi[5] = Cc[1]; lo[6] = Cc[2]; hi[6] = Cc[3]; }
+        else { lo[0] = A[0]; hi[0] = A[1]; lo[1] = A[2]; hi[1] = A[3]; lo[2] = B[0]; hi[2] = B[1]; lo[3] = B[2]; hi[3] = B[3]; lo[4] = Cc[0]; hi[4] = Cc[1]; lo[5] = Cc[2]; hi[5] = Cc[3]; lo[6] = 0; hi[6] = 0; }
+        D3 p1 = mk(u64_to_m1_1(lo[0], hi[0]), u64_to_m1_1(lo[1], hi[1]), u64_to_m1_1(lo[2], hi[2]));
+        D3 p2 = mk(u64_to_m1_1(lo[3], hi[3]), u64_to_m1_1(lo[4], hi[4]), u64_to_m1_1(lo[5], hi[5]));
+        const bool a1 = length_squared(p1) < 1.0, a2 = length_squared(p2) < 1.0;
+        const uint32_t used = a1 ? 3u : 6u;                       // draws consumed by this trip
+        // stream position in u64 units before the trip: 2*blk - has; advance it and rebuild (blk, has, cached)
+        const uint32_t pos = 2u * g.blk - g.has + used;
+        g.blk = (pos + 1u) >> 1;
+        g.has = pos & 1u;
+        g.c_lo = a1 ? lo[3] : lo[6]; g.c_hi = a1 ? hi[3] : hi[6];   // the next unread draw; it is a block's second half exactly when pos is odd
+        if (a1) return p1;
+        if (a2) return p2;
+    }
+}
 RT_DEV D3 random_in_unit_sphere(Rng& g, uint32_t k0, uint32_t k1) {                                           // point3d.rs:22-38
     for (;;) {
         double x = rng_m1_1(g, k0, k1), y = rng_m1_1(g, k0, k1), z = rng_m1_1(g, k0, k1);

@@ -15,9 +15,18 @@ constexpr int kCtasPerSm = 2;        // lane-autonomous kernel (rt_trace_kernel)
 #endif
 constexpr int kWfThreadsPerSm = RT_WF_THREADS;  // CTA-wavefront kernel (rt_wavefront_kernel): resident threads per SM the register budget targets
 constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory (lanes kernel)
-constexpr int kClusterK = 4;       // spheres per second-level cluster (slots, padded)
-constexpr int kWfMaxClus = 32;     // wavefront kernel: per-thread list of candidate clusters / first-level candidates
-constexpr int kWfMaxCand = 16;     // wavefront kernel, two-level mode: per-thread list of second-level (sphere) candidates
+#ifndef RT_CLUSTER_K
+#define RT_CLUSTER_K 4
+#endif
+constexpr int kClusterK = RT_CLUSTER_K;       // spheres per second-level cluster (slots, padded)
+#ifndef RT_WF_MAXCLUS
+#define RT_WF_MAXCLUS 32
+#endif
+#ifndef RT_WF_MAXCAND
+#define RT_WF_MAXCAND 16
+#endif
+constexpr int kWfMaxClus = RT_WF_MAXCLUS;     // wavefront kernel: per-thread list of candidate clusters / first-level candidates
+constexpr int kWfMaxCand = RT_WF_MAXCAND;     // wavefront kernel, two-level mode: per-thread list of second-level (sphere) candidates
 
 // 32-byte material record (device copy of the material half of rt_sphere)
 struct DevMat { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };

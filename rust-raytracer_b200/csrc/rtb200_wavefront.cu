@@ -22,6 +22,16 @@
 
 using namespace rtd;
 
+#ifndef RT_L1_GUARD
+#define RT_L1_GUARD 0
+#endif
+#ifndef RT_SAMPLE_ILP
+#define RT_SAMPLE_ILP 1   // two rejection trials per trip with their Philox blocks computed together (bit-identical stream)
+#endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 3   // albedo-stack levels kept in shared memory per slot (deeper levels live in global memory)
+#endif
+
 namespace rtk {
 
 namespace {
@@ -34,6 +44,7 @@ struct WfSmem {
     uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each
     uint32_t bi, work, pix, smp, blk, clo, chi, lvl, shd;   // uint32[kBlock] each
     uint32_t perm;                                  // uint16[kBlock]
+    uint32_t stk;                                   // uint32[RT_SMEM_STACK][kBlock]: first levels of the albedo stack
     uint32_t cnt;                                   // uint32[2][8]
     uint32_t flags;                                 // uint32[4]
     uint32_t total;
@@ -59,6 +70,7 @@ __host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32
     L.bi = off; off += kBlock * 4u; L.work = off; off += kBlock * 4u; L.pix = off; off += kBlock * 4u; L.smp = off; off += kBlock * 4u;
     L.blk = off; off += kBlock * 4u; L.clo = off; off += kBlock * 4u; L.chi = off; off += kBlock * 4u; L.lvl = off; off += kBlock * 4u; L.shd = off; off += kBlock * 4u;
     L.perm = off; off += kBlock * 2u;
+    L.stk = off; off += (uint32_t)RT_SMEM_STACK * kBlock * 4u;
     L.cnt = off; off += 2u * 8u * 4u;
     L.flags = off; off += 16u;
     L.total = off;
@@ -114,6 +126,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     uint32_t* s_chi = reinterpret_cast<uint32_t*>(smem_raw + L.chi); uint32_t* s_lvl = reinterpret_cast<uint32_t*>(smem_raw + L.lvl);
     uint32_t* s_shd = reinterpret_cast<uint32_t*>(smem_raw + L.shd);   // depth of the shadow-frame stack (0 = main path)
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + L.perm);
+    uint32_t* s_stk = reinterpret_cast<uint32_t*>(smem_raw + L.stk);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + L.cnt);
     volatile uint32_t* s_flags = reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags);   // [0] = queue exhausted
 
@@ -122,6 +135,12 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     const unsigned FULL = 0xffffffffu;
     const uint32_t k0 = p.key0, k1 = p.key1;
     const uint32_t stack_col = blockIdx.x * kBlock;   // this CTA's columns of the albedo stack
+    auto stack_push = [&](uint32_t lvl, uint32_t s, uint32_t code) {
+        if (lvl < (uint32_t)RT_SMEM_STACK) s_stk[lvl * kBlock + s] = code; else p.stack[(size_t)lvl * p.stack_stride + stack_col + s] = code;
+    };
+    auto stack_get = [&](uint32_t lvl, uint32_t s) -> uint32_t {
+        return lvl < (uint32_t)RT_SMEM_STACK ? s_stk[lvl * kBlock + s] : p.stack[(size_t)lvl * p.stack_stride + stack_col + s];
+    };
 
     // ---- stage the scene into shared memory (TMA bulk copies, one mbarrier) ----
     if (tid == 0) mbar_init(bar, 1);
@@ -279,8 +298,14 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                         float2 Dv[4];
                         const float4* rec = s_filt + 2 * pp;
                         RT_FILTER_PAIRS(rec, Dv, 4)
-                        float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
-                        if (m >= thr) {   // rare: some lane has a candidate among these 8 records
+                        // Without clustering a block rarely holds a candidate, so one max-reduction + branch guards the appends; with
+                        // clustering some lane of the warp hits nearly every block of cluster bounds, so the guard is dropped.
+                        bool any_hit = true;
+                        if (!TWO || RT_L1_GUARD) {
+                            float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
+                            any_hit = m >= thr;
+                        }
+                        if (any_hit) {
                             const uint32_t j0 = 2u * pp;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -426,8 +451,9 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                     D3 nd = d;
                     bool absorbed = false;
                     const bool is_light = (c == CLS_LIGHT);                         // materials.rs:65-69: Some((None, white))
+                    D3 rs = mk(0, 0, 0);
+                    if (c == CLS_DIFFUSE || c == CLS_METAL) rs = RT_SAMPLE_ILP ? random_in_unit_sphere_ilp(rng, k0, k1) : random_in_unit_sphere(rng, k0, k1);   // one rejection loop for a warp that straddles both classes
                     if (c == CLS_DIFFUSE) {                                         // materials.rs:84-95, 256-267
-                        D3 rs = random_in_unit_sphere(rng, k0, k1);
                         D3 sd = add(h.normal, rs);
                         if (near_zero(sd)) sd = h.normal;
                         D3 target = add(h.point, sd);
@@ -438,7 +464,6 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                             code = 0x80000000u | texture_texel(p.tex[m.tex], m.param, tu, tv);
                         }
                     } else if (c == CLS_METAL) {                                    // materials.rs:115-129
-                        D3 rs = random_in_unit_sphere(rng, k0, k1);
                         D3 refl = reflect(d, h.normal);
                         nd = add(refl, mul(rs, m.param));
                         if (!(dot(nd, h.normal) > 0.0)) absorbed = true;            // None -> black, no light test (raytracer.rs:127-131)
@@ -479,7 +504,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                         } else if (shd == 0u) {
                             if (is_light) { cr = 1.f; cg = 1.f; cb = 1.f; done = true; }   // `None => albedo` (raytracer.rs:124)
                             else {
-                                p.stack[(size_t)level * p.stack_stride + stack_col + s] = code;
+                                stack_push(level, s, code);
                                 ++level;
                                 o = h.point; d = nd;
                                 if (level == p.max_depth) done = true;   // the next ray_color call returns black (raytracer.rs:80-82)
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                                     p.lterm[(size_t)(level * 3u + 0u) * p.stack_stride + stack_col + s] = Lr;   // level is 0 or 1 here
                                     p.lterm[(size_t)(level * 3u + 1u) * p.stack_stride + stack_col + s] = Lg;
                                     p.lterm[(size_t)(level * 3u + 2u) * p.stack_stride + stack_col + s] = Lb;
-                                    p.stack[(size_t)level * p.stack_stride + stack_col + s] = f.code;
+                                    stack_push(level, s, f.code);
                                     ++level;
                                     o = mk(f.px, f.py, f.pz); d = mk(f.ndx, f.ndy, f.ndz);
                                     if (level == p.max_depth) done = true;
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                     if (LIGHTS || cr != 0.f || cg != 0.f || cb != 0.f) {
                         for (int l = (int)level - 1; l >= 0; --l) {
                             float ar, ag, ab;
-                            albedo_of(p.stack[(size_t)l * p.stack_stride + stack_col + s], mat, ar, ag, ab);
+                            albedo_of(stack_get((uint32_t)l, s), mat, ar, ag, ab);
                             float Lr = 0.f, Lg = 0.f, Lb = 0.f;
                             if (LIGHTS && l < 2) {
                                 Lr = p.lterm[(size_t)(l * 3 + 0) * p.stack_stride + stack_col + s];
