@@ -73,7 +73,10 @@ def gather_frame(shard: torch.Tensor, height: int, world: int, band_rows: int, r
 
 
 class DistributedRenderer:
-    """Scene resident on this rank's GPU; render() = trace the rank's rows, gather RGB8 to rank 0."""
+    """Scene resident on this rank's GPU; a frame = trace the rank's rows, gather RGB8 to rank 0.
+
+    In a frame loop (`render_async`) the gather of frame k runs on a side stream while frame k+1 is already tracing:
+    the shard buffers are double-buffered, so the only exchange step of the path never sits on the critical path."""
 
     def __init__(self, scene: Scene, band_rows: int = 1, variant: int = 0):
         self.rank, self.world, self.local = env_rank_world()
@@ -86,12 +89,18 @@ class DistributedRenderer:
         self.resident = ResidentScene(scene, self.opts)
         self.rows = self.resident.rows
         self.rows_max = padded_rows(self.h, self.world, band_rows)
-        self.shard = torch.zeros((self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device)
+        self.shards = [torch.zeros((self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.shard = self.shards[0]
         self.frame = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device) if self.rank == 0 else None
         self.gbuf = torch.empty((self.world, self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) if (self.rank == 0 and self.world > 1) else None
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._traced = [torch.cuda.Event() for _ in range(2)]     # shard k has been written by resolve
+        self._gathered = [torch.cuda.Event() for _ in range(2)]   # shard k has been consumed by the gather
+        self._frame_no = 0
 
     def render(self) -> dict:
-        """One frame on the current torch stream. Returns this rank's stats; rank 0's `frame` holds the image."""
+        """One frame on the current torch stream, blocking. Returns this rank's stats; rank 0's `frame` holds the image."""
+        self.shard = self.shards[0]
         st = self.resident.render(self.shard.data_ptr(), 0, _torch_stream())
         if self.world > 1:
             gather_frame(self.shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
@@ -100,14 +109,27 @@ class DistributedRenderer:
         return st
 
     def render_async(self):
-        """Enqueue one frame (trace + resolve + gather) on the current torch stream without waiting; wait() collects stats."""
-        self.resident.render_async(self.shard.data_ptr(), 0, _torch_stream())
+        """Enqueue one frame without waiting: trace + resolve on the current stream, gather on the side stream."""
+        k = self._frame_no & 1
+        self._frame_no += 1
+        cur = torch.cuda.current_stream()
+        shard = self.shards[k]
+        if self.world > 1 and self._frame_no > 2:
+            cur.wait_event(self._gathered[k])                   # the gather two frames ago has finished reading this shard
+        self.resident.render_async(shard.data_ptr(), 0, _torch_stream())
+        self.shard = shard
         if self.world > 1:
-            gather_frame(self.shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
+            self._traced[k].record(cur)
+            self.comm_stream.wait_event(self._traced[k])
+            with torch.cuda.stream(self.comm_stream):
+                gather_frame(shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
+                self._gathered[k].record(self.comm_stream)
         else:
-            self.frame = self.shard[: self.h]
+            self.frame = shard[: self.h]
 
     def wait(self) -> dict:
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
         return self.resident.wait()
 
     def release(self):

@@ -26,6 +26,13 @@ def main():
         if rank == 0:
             full, st_full = R.render_rgb8(sc, R.make_options(device=local))
             ok = ok and np.array_equal(rdr.frame.cpu().numpy(), full) and int(rays.item()) == st_full["rays"]
+        # frame loop without host waits: gathers overlap the next frame on a side stream, shards are double-buffered
+        for _ in range(5):
+            rdr.render_async()
+        st2 = rdr.wait()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ok = ok and np.array_equal(rdr.frame.cpu().numpy(), full) and st2["frames"] == 5
         rdr.release()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

@@ -217,7 +217,13 @@ def test_resident_scene_renders_into_device_buffers():
     st = rs.render(out.data_ptr(), lin.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().reshape(90, 120, 3), ref) and st["rays"] == st0["rays"]
-    assert st["kernel_launches"] == 2 and st["device_ms"] > 0
+    assert st["kernel_launches"] == 2 and st["device_ms"] > 0 and st["frames"] == 1
+    out.zero_()
+    for _ in range(4):                     # non-blocking frame loop
+        rs.render_async(out.data_ptr(), 0, 0)
+    st4 = rs.wait()
+    assert st4["frames"] == 4 and st4["kernel_launches"] == 8 and st4["rays"] == st0["rays"] and st4["trace_ms"] > 0
+    assert np.array_equal(out.cpu().numpy().reshape(90, 120, 3), ref)
     rs.release()
 
 
