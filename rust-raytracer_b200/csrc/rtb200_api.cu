@@ -52,7 +52,10 @@ struct DeviceCtx {
     int sm_count = 0;
     size_t max_smem = 0;
     cudaStream_t stream = nullptr;
-    GrowBuf samplebuf, accum, stack, small, out_rgb8, out_lin, probe, frames, lterm;
+    // Two sets of per-frame work buffers: a frame loop that alternates two streams lets frame k+1 start tracing while frame k
+    // drains its last paths and resolves (rtb200_render_device_async); blocking calls use set 0 only.
+    struct WorkSet { GrowBuf samplebuf, accum, stack, small, frames, lterm; } ws[2];
+    GrowBuf out_rgb8, out_lin, probe;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 };
@@ -120,7 +123,11 @@ struct rtb200_scene_t {
     size_t smem = 0;
     uint32_t spp_batch = 0;
     std::vector<void*> owned;   // device allocations owned by the handle
-    cudaStream_t last_stream = nullptr;   // stream, batch and launch count of the most recently enqueued frame
+    cudaStream_t last_stream = nullptr;   // stream, work set, batch and launch count of the most recently enqueued frame
+    int last_set = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};   // distinct streams used by the pending frames
+    int n_streams = 0;
+    uint32_t frame_counter = 0;
     uint32_t last_batches = 0, last_launches = 0;
     uint32_t pending_frames = 0;          // frames enqueued since the last wait (their events sit in the context's event ring)
     uint64_t h2d_bytes = 0;
@@ -489,34 +496,36 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
 }
 
 // Enqueue one frame on `stream_in` (or the context's stream) without waiting for it.
-static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in) {
+static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, int set) {
     if (!h) return fail(RT_ERR_INVALID, "null scene handle");
     DeviceCtx* ctx = h->ctx;
+    DeviceCtx::WorkSet& W = ctx->ws[set & 1];
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream_in ? (cudaStream_t)stream_in : ctx->stream;
     TraceParams tp = h->tp;
-    h->last_stream = st; h->last_batches = 0; h->last_launches = 0;
+    h->last_stream = st; h->last_set = set & 1; h->last_batches = 0; h->last_launches = 0;
+    if (h->n_streams < 2 && (h->n_streams == 0 || h->streams[0] != st)) h->streams[h->n_streams++] = st;
     if (tp.npix_local == 0) return RT_OK;
 
     const uint32_t spp = tp.spp, spb = h->spp_batch;
     const uint32_t n_batches = (spp + spb - 1) / spb;
     const uint32_t threads_total = (uint32_t)h->grid * (uint32_t)(h->lanes ? kBlock : h->block);
 
-    CU(ctx->samplebuf.ensure((size_t)spb * tp.npix_local * 16));
-    CU(ctx->accum.ensure((size_t)tp.npix_local * 12));
-    CU(ctx->stack.ensure((size_t)std::max<uint32_t>(tp.max_depth, 1) * threads_total * 4));
-    CU(ctx->small.ensure(256 + (size_t)n_batches * 4));
+    CU(W.samplebuf.ensure((size_t)spb * tp.npix_local * 16));
+    CU(W.accum.ensure((size_t)tp.npix_local * 12));
+    CU(W.stack.ensure((size_t)std::max<uint32_t>(tp.max_depth, 1) * threads_total * 4));
+    CU(W.small.ensure(256 + (size_t)n_batches * 4));
     if (tp.n_lights > 0) {
         // Nested light tests form a branching process: a vertex nests with probability 0.1 n and then spawns n shadow rays, so
         // depth d is reached with probability ~(0.1 n^2 P_hit)^d: harmless for 1-2 lights, near-critical for 3 (the reference
         // itself recurses hundreds of frames deep there) and super-critical beyond. Size the per-path frame stack accordingly;
         // an overflow is reported as an error, never rendered wrongly.
         tp.max_shadow = tp.n_lights == 1 ? 32u : tp.n_lights == 2 ? 96u : 384u;
-        CU(ctx->frames.ensure((size_t)tp.max_shadow * threads_total * sizeof(ShadowFrame)));
-        CU(ctx->lterm.ensure((size_t)6 * threads_total * 4));
+        CU(W.frames.ensure((size_t)tp.max_shadow * threads_total * sizeof(ShadowFrame)));
+        CU(W.lterm.ensure((size_t)6 * threads_total * 4));
     }
-    tp.frames = (ShadowFrame*)ctx->frames.p;
-    tp.lterm = (float*)ctx->lterm.p;
+    tp.frames = (ShadowFrame*)W.frames.p;
+    tp.lterm = (float*)W.lterm.p;
     // event ring: every pending frame owns 2 + 2*n_batches events (begin, end, and a pair around each trace launch)
     const uint32_t kRing = 64, per_frame = 2 + 2 * n_batches;
     if (h->pending_frames >= kRing) return fail(RT_ERR_INVALID, "more than 64 frames enqueued without rtb200_render_device_wait");
@@ -524,12 +533,12 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
         cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
     }
     cudaEvent_t* fev = ctx->ev.data() + (size_t)h->pending_frames * per_frame;
-    unsigned long long* stat = (unsigned long long*)ctx->small.p;
-    unsigned int* counters = (unsigned int*)((char*)ctx->small.p + 256);
-    CU(cudaMemsetAsync(ctx->small.p, 0, 256 + (size_t)n_batches * 4, st));
+    unsigned long long* stat = (unsigned long long*)W.small.p;
+    unsigned int* counters = (unsigned int*)((char*)W.small.p + 256);
+    CU(cudaMemsetAsync(W.small.p, 0, 256 + (size_t)n_batches * 4, st));
 
-    tp.samplebuf = (float4*)ctx->samplebuf.p;
-    tp.stack = (uint32_t*)ctx->stack.p;
+    tp.samplebuf = (float4*)W.samplebuf.p;
+    tp.stack = (uint32_t*)W.stack.p;
     tp.stack_stride = threads_total;
     tp.stat = stat;
 
@@ -550,7 +559,7 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
         }
         CU(cudaEventRecord(fev[3 + 2 * b], st));
         ResolveParams q{};
-        q.samplebuf = tp.samplebuf; q.accum = (float*)ctx->accum.p; q.npix_local = tp.npix_local; q.s_count = tp.s_count;
+        q.samplebuf = tp.samplebuf; q.accum = (float*)W.accum.p; q.npix_local = tp.npix_local; q.s_count = tp.s_count;
         q.first = b == 0; q.last = b + 1 == n_batches; q.spp = spp;
         q.out_linear = (float*)dev_linear_f32; q.out_rgb8 = (uint8_t*)dev_rgb8;
         CU(launch_resolve(q, st));
@@ -570,9 +579,11 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
     if (stats) memset(stats, 0, sizeof *stats);
     if (h->tp.npix_local == 0 || h->last_batches == 0 || h->pending_frames == 0) return RT_OK;
     cudaStream_t st = h->last_stream;
+    DeviceCtx::WorkSet& W = ctx->ws[h->last_set];
     unsigned long long hstat[16] = {0};
-    CU(cudaMemcpyAsync(hstat, ctx->small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpyAsync(hstat, W.small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < h->n_streams; ++i) CU(cudaStreamSynchronize(h->streams[i]));
+    h->n_streams = 0;
     if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
     if (stats) {
         // device_ms / trace_ms: summed over every frame enqueued since the previous wait; the counters are the last frame's
@@ -599,7 +610,8 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
 
 int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, rt_stats* stats) {
     auto wall0 = std::chrono::steady_clock::now();
-    int rc = render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in);
+    if (h && h->pending_frames) { int rcw = render_collect(h, nullptr); if (rcw != RT_OK) return rcw; }   // drain frames enqueued earlier
+    int rc = render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in, 0);
     if (rc != RT_OK) return rc;
     rc = render_collect(h, stats);
     if (rc == RT_OK && stats) stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
@@ -607,7 +619,8 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
 }
 
 int rtb200_render_device_async(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in) {
-    return render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in);
+    if (!h) return fail(RT_ERR_INVALID, "null scene handle");
+    return render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in, (int)(h->frame_counter++ & 1u));
 }
 
 int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats) { return render_collect(h, stats); }

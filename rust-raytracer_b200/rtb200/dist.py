@@ -94,6 +94,7 @@ class DistributedRenderer:
         self.frame = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device) if self.rank == 0 else None
         self.gbuf = torch.empty((self.world, self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) if (self.rank == 0 and self.world > 1) else None
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self.frame_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]   # consecutive frames alternate streams
         self._traced = [torch.cuda.Event() for _ in range(2)]     # shard k has been written by resolve
         self._gathered = [torch.cuda.Event() for _ in range(2)]   # shard k has been consumed by the gather
         self._frame_no = 0
@@ -109,17 +110,21 @@ class DistributedRenderer:
         return st
 
     def render_async(self):
-        """Enqueue one frame without waiting: trace + resolve on the current stream, gather on the side stream."""
+        """Enqueue one frame without waiting. Frames alternate between two streams (and two shard buffers, and the
+        library's two work-buffer sets), so frame k+1 starts tracing while frame k drains its last paths, resolves and
+        is gathered on the side stream."""
         k = self._frame_no & 1
         self._frame_no += 1
         cur = torch.cuda.current_stream()
+        fs = self.frame_streams[k]
+        fs.wait_stream(cur)                                      # whatever the caller enqueued before this frame
         shard = self.shards[k]
         if self.world > 1 and self._frame_no > 2:
-            cur.wait_event(self._gathered[k])                   # the gather two frames ago has finished reading this shard
-        self.resident.render_async(shard.data_ptr(), 0, _torch_stream())
+            fs.wait_event(self._gathered[k])                    # the gather two frames ago has finished reading this shard
+        self.resident.render_async(shard.data_ptr(), 0, fs.cuda_stream)
         self.shard = shard
         if self.world > 1:
-            self._traced[k].record(cur)
+            self._traced[k].record(fs)
             self.comm_stream.wait_event(self._traced[k])
             with torch.cuda.stream(self.comm_stream):
                 gather_frame(shard, self.h, self.world, self.band_rows, self.rank, self.frame, self.gbuf)
@@ -127,9 +132,16 @@ class DistributedRenderer:
         else:
             self.frame = shard[: self.h]
 
-    def wait(self) -> dict:
+    def join(self):
+        """Make the current stream wait for every frame enqueued so far (and its gather)."""
+        cur = torch.cuda.current_stream()
+        for fs in self.frame_streams:
+            cur.wait_stream(fs)
         if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            cur.wait_stream(self.comm_stream)
+
+    def wait(self) -> dict:
+        self.join()
         return self.resident.wait()
 
     def release(self):
