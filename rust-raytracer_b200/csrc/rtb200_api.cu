@@ -123,6 +123,9 @@ struct rtb200_scene_t {
     size_t smem = 0;
     uint32_t spp_batch = 0;
     std::vector<void*> owned;   // device allocations owned by the handle
+    struct Upload { const void* src; size_t bytes; void** field; };
+    std::vector<Upload> uploads;         // pending scene arrays (commit_uploads)
+    std::vector<uint8_t> staging;        // host image of the device arena
     cudaStream_t last_stream = nullptr;   // stream, work set, batch and launch count of the most recently enqueued frame
     int last_set = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};   // distinct streams used by the pending frames
@@ -167,25 +170,42 @@ uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_
     return rows;
 }
 
+static int render_collect(rtb200_scene_handle h, rt_stats* stats);
+
 int rtb200_scene_release(rtb200_scene_handle h) {
     if (!h) return RT_OK;
     if (h->device >= 0) cudaSetDevice(h->device);
+    if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
     for (void* p : h->owned) cudaFree(p);
     delete h;
     return RT_OK;
 }
 
-static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** dev) {
-    *dev = nullptr;
+// Scene arrays are collected first and then placed in ONE device arena filled by ONE host->device copy
+// (a per-frame upload costs one cudaMalloc, one copy, one cudaFree). `field` is patched with the device address.
+static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** field) {
+    *field = nullptr;
     if (bytes == 0) bytes = 16;
-    void* d = nullptr;
-    CU(cudaMalloc(&d, bytes));
-    h->owned.push_back(d);
-    if (src) {
-        CU(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->ctx->stream));
-        h->h2d_bytes += bytes;
+    h->uploads.push_back(rtb200_scene_t::Upload{src, bytes, field});
+    return RT_OK;
+}
+
+static int commit_uploads(rtb200_scene_t* h) {
+    size_t total = 0;
+    for (auto& u : h->uploads) total += (u.bytes + 255) & ~(size_t)255;
+    void* base = nullptr;
+    CU(cudaMalloc(&base, total ? total : 256));
+    h->owned.push_back(base);
+    size_t off = 0;
+    for (auto& u : h->uploads) { *u.field = (char*)base + off; off += (u.bytes + 255) & ~(size_t)255; }   // addresses first: tables may hold them
+    h->staging.assign(total, 0);
+    off = 0;
+    for (auto& u : h->uploads) {
+        if (u.src) { memcpy(h->staging.data() + off, u.src, u.bytes); h->h2d_bytes += u.bytes; }
+        off += (u.bytes + 255) & ~(size_t)255;
     }
-    *dev = d;
+    if (total) CU(cudaMemcpyAsync(base, h->staging.data(), total, cudaMemcpyHostToDevice, h->ctx->stream));
+    h->uploads.clear();
     return RT_OK;
 }
 
@@ -388,50 +408,38 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     tp.two_level = two_level ? 1u : 0u;
     tp.n_clusters = n_clusters;
     if (two_level) {
-        if ((rc = upload_array(h, cfilt.data(), cfilt.size() * 4, &d)) != RT_OK) return rc;
-        tp.filt = (const float4*)d;
-        if ((rc = upload_array(h, sfilt.data(), sfilt.size() * 4, &d)) != RT_OK) return rc;
-        tp.sfilt = (const float4*)d;
-        if ((rc = upload_array(h, orig.data(), orig.size() * 2, &d)) != RT_OK) return rc;
-        tp.orig = (const uint16_t*)d;
-        if ((rc = upload_array(h, cmeta.data(), cmeta.size() * 4, &d)) != RT_OK) return rc;
-        tp.cmeta = (const float*)d;
+        if ((rc = upload_array(h, cfilt.data(), cfilt.size() * 4, (void**)&tp.filt)) != RT_OK) return rc;
+        if ((rc = upload_array(h, sfilt.data(), sfilt.size() * 4, (void**)&tp.sfilt)) != RT_OK) return rc;
+        if ((rc = upload_array(h, orig.data(), orig.size() * 2, (void**)&tp.orig)) != RT_OK) return rc;
+        if ((rc = upload_array(h, cmeta.data(), cmeta.size() * 4, (void**)&tp.cmeta)) != RT_OK) return rc;
         n_pairs = n_cpairs;    // the first-level scan loop runs over the cluster records
     } else {
-        if ((rc = upload_array(h, filt.data(), filt.size() * 4, &d)) != RT_OK) return rc;
-        tp.filt = (const float4*)d;
+        if ((rc = upload_array(h, filt.data(), filt.size() * 4, (void**)&tp.filt)) != RT_OK) return rc;
         tp.sfilt = nullptr; tp.orig = nullptr; tp.cmeta = nullptr;
     }
-    if ((rc = upload_array(h, geo.data(), geo.size() * 8, &d)) != RT_OK) return rc;
-    tp.geo = (const double4*)d;
-    if ((rc = upload_array(h, mat.data(), mat.size() * sizeof(DevMat), &d)) != RT_OK) return rc;
-    tp.mat = (const DevMat*)d;
+    if ((rc = upload_array(h, geo.data(), geo.size() * 8, (void**)&tp.geo)) != RT_OK) return rc;
+    if ((rc = upload_array(h, mat.data(), mat.size() * sizeof(DevMat), (void**)&tp.mat)) != RT_OK) return rc;
 
     std::vector<rtd::DevTex> texs(std::max<uint64_t>(s->n_textures, 1));
     for (uint64_t t = 0; t < s->n_textures; ++t) {
         const rt_image& im = s->textures[t];
         texs[t].rgb8 = nullptr; texs[t].width = im.width; texs[t].height = im.height;
         if (im.rgb8 && im.width && im.height) {
-            if ((rc = upload_array(h, im.rgb8, im.width * im.height * 3, &d)) != RT_OK) return rc;
-            texs[t].rgb8 = (const uint8_t*)d;
+            if ((rc = upload_array(h, im.rgb8, im.width * im.height * 3, (void**)&texs[t].rgb8)) != RT_OK) return rc;
         }
     }
-    if ((rc = upload_array(h, texs.data(), texs.size() * sizeof(rtd::DevTex), &d)) != RT_OK) return rc;
-    tp.tex = (const rtd::DevTex*)d;
+    if ((rc = upload_array(h, texs.data(), texs.size() * sizeof(rtd::DevTex), (void**)&tp.tex)) != RT_OK) return rc;
     tp.sky_mode = s->sky.mode;
     tp.sky.rgb8 = nullptr; tp.sky.width = 0; tp.sky.height = 0;
     if (s->sky.mode == RT_SKY_TEXTURE) {
-        if ((rc = upload_array(h, s->sky.tex.rgb8, s->sky.tex.width * s->sky.tex.height * 3, &d)) != RT_OK) return rc;
-        tp.sky.rgb8 = (const uint8_t*)d; tp.sky.width = s->sky.tex.width; tp.sky.height = s->sky.tex.height;
+        if ((rc = upload_array(h, s->sky.tex.rgb8, s->sky.tex.width * s->sky.tex.height * 3, (void**)&tp.sky.rgb8)) != RT_OK) return rc;
+        tp.sky.width = s->sky.tex.width; tp.sky.height = s->sky.tex.height;
     }
 
-    {
-        std::vector<uint32_t> lights;
-        for (uint32_t i = 0; i < n; ++i) if (s->spheres[i].kind == RT_LIGHT) lights.push_back(i);
-        lights.push_back(0);
-        if ((rc = upload_array(h, lights.data(), lights.size() * 4, &d)) != RT_OK) return rc;
-        tp.lights = (const uint32_t*)d;
-    }
+    std::vector<uint32_t> lights;
+    for (uint32_t i = 0; i < n; ++i) if (s->spheres[i].kind == RT_LIGHT) lights.push_back(i);
+    lights.push_back(0);
+    if ((rc = upload_array(h, lights.data(), lights.size() * 4, (void**)&tp.lights)) != RT_OK) return rc;
     tp.n = n; tp.n_pairs = n_pairs; tp.n_lights = n_lights;
     tp.gx = g[0]; tp.gy = g[1]; tp.gz = g[2];
     tp.er_coef = 1.0f - (float)(96.0 * U);
@@ -489,6 +497,7 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     while (spb > 1 && spb * tp.npix_local >= (1ull << 31)) spb /= 2;
     h->spp_batch = (uint32_t)spb;
 
+    if ((rc = commit_uploads(h)) != RT_OK) return rc;
     CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
     guard.ok = true;
     *out = h;
@@ -584,6 +593,7 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
     CU(cudaMemcpyAsync(hstat, W.small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
     for (int i = 0; i < h->n_streams; ++i) CU(cudaStreamSynchronize(h->streams[i]));
     h->n_streams = 0;
+    if (hstat[5] != 0) { h->pending_frames = 0; }
     if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
     if (stats) {
         // device_ms / trace_ms: summed over every frame enqueued since the previous wait; the counters are the last frame's
