@@ -165,6 +165,14 @@ int rtb200_scene_release(rtb200_scene_handle h);
 int  rtb200_decode_jpeg_file(const char* path, uint8_t** out_rgb8, uint64_t* width, uint64_t* height);
 void rtb200_free(void* p);
 
+/* Diagnostic, host only (no GPU needed): the conservative filter records the closest-hit stage of hit_world (raytracer.rs:44-59)
+ * would use for `scene`: recentring offset, first level (pair-packed {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}: cluster bounds, or the spheres
+ * themselves), second level (member spheres, cluster_size slots per cluster), slot -> sphere index, |c| of each bound.
+ * info = {two_level, first_level_pairs, n_clusters, cluster_size}. Arrays are filled up to their capacities (elements). */
+int rtb200_debug_filter_records(const rt_scene* scene, uint32_t variant, double recentre[3], uint32_t info[4],
+                                float* first, uint64_t cap_first, float* second, uint64_t cap_second,
+                                uint16_t* slot_to_sphere, uint64_t cap_slots, float* cluster_abs, uint64_t cap_clusters);
+
 /* Device-function probes: run the kernel's own device routines on one thread and return the result,
  * so the reference's known-answer tests can be asserted against the GPU code itself.
  *   sphere.rs:81-88, materials.rs:157-174, raytracer.rs:167-189, camera.rs:105-122 */

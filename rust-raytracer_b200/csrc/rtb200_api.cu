@@ -136,126 +136,26 @@ struct rtb200_scene_t {
     uint64_t h2d_bytes = 0;
 };
 
-extern "C" {
-
-int rtb200_abi_version(void) { return RTB200_ABI_VERSION; }
-const char* rtb200_last_error(void) { return g_last_error.c_str(); }
-
-// Camera::new — camera.rs:45-77. Host, once per frame, f64, same operation order as the reference.
-// (Compiled with -fmad=false / no host contraction: see the Makefile.)
-int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out) {
-    if (!p || !out) return fail(RT_ERR_INVALID, "null argument");
-    const double PI = 3.14159265358979323846264338327950288;
-    double theta = p->vfov_deg * (PI / 180.0);
-    double half_height = std::tan(theta / 2.0);
-    double half_width = p->aspect * half_height;
-    V3 look_from = v3(p->look_from), look_at = v3(p->look_at), vup = v3(p->vup);
-    V3 w = vunit(look_from - look_at);
-    V3 u = vunit(vcross(vup, w));
-    V3 v = vcross(w, u);
-    V3 origin = look_from;
-    V3 llc = origin - (u * half_width) - (v * half_height) - w;
-    V3 horizontal = u * 2.0 * half_width;
-    V3 vertical = v * 2.0 * half_height;
-    out->origin = rv(origin); out->lower_left_corner = rv(llc); out->horizontal = rv(horizontal); out->vertical = rv(vertical);
-    return RT_OK;
-}
-
-uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_t band_rows) {
-    if (world <= 1) return height;
-    if (band_rows == 0) band_rows = 1;
-    uint32_t rows = 0;
-    for (uint32_t y = 0; y < height; ++y)
-        if ((int32_t)((y / band_rows) % (uint32_t)world) == rank) ++rows;
-    return rows;
-}
-
-static int render_collect(rtb200_scene_handle h, rt_stats* stats);
-
-int rtb200_scene_release(rtb200_scene_handle h) {
-    if (!h) return RT_OK;
-    if (h->device >= 0) cudaSetDevice(h->device);
-    if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
-    for (void* p : h->owned) cudaFree(p);
-    delete h;
-    return RT_OK;
-}
-
-// Scene arrays are collected first and then placed in ONE device arena filled by ONE host->device copy
-// (a per-frame upload costs one cudaMalloc, one copy, one cudaFree). `field` is patched with the device address.
-static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** field) {
-    *field = nullptr;
-    if (bytes == 0) bytes = 16;
-    h->uploads.push_back(rtb200_scene_t::Upload{src, bytes, field});
-    return RT_OK;
-}
-
-static int commit_uploads(rtb200_scene_t* h) {
-    size_t total = 0;
-    for (auto& u : h->uploads) total += (u.bytes + 255) & ~(size_t)255;
-    void* base = nullptr;
-    CU(cudaMalloc(&base, total ? total : 256));
-    h->owned.push_back(base);
-    size_t off = 0;
-    for (auto& u : h->uploads) { *u.field = (char*)base + off; off += (u.bytes + 255) & ~(size_t)255; }   // addresses first: tables may hold them
-    h->staging.assign(total, 0);
-    off = 0;
-    for (auto& u : h->uploads) {
-        if (u.src) { memcpy(h->staging.data() + off, u.src, u.bytes); h->h2d_bytes += u.bytes; }
-        off += (u.bytes + 255) & ~(size_t)255;
-    }
-    if (total) CU(cudaMemcpyAsync(base, h->staging.data(), total, cudaMemcpyHostToDevice, h->ctx->stream));
-    h->uploads.clear();
-    return RT_OK;
-}
-
-int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
-    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
-    *out = nullptr;
-    rt_options opts{};
-    opts.device = -1; opts.rank = 0; opts.world = 1; opts.band_rows = 1; opts.variant = RT_VARIANT_AUTO;
-    if (opts_in) opts = *opts_in;
-    if (opts.world <= 0) opts.world = 1;
-    if (opts.band_rows == 0) opts.band_rows = 1;
-    if (opts.rank < 0 || opts.rank >= opts.world) return fail(RT_ERR_INVALID, "rank outside [0, world)");
-    if (opts.flags != 0) return fail(RT_ERR_INVALID, "flags must be 0");
-    if (s->width < 2 || s->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by w-1, h-1: raytracer.rs:199-200)");
-    if (s->samples_per_pixel == 0) return fail(RT_ERR_INVALID, "samples_per_pixel must be > 0");
-    if ((uint64_t)s->width * s->height >= (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
-    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
-    if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
-
-    uint32_t n = (uint32_t)s->n_spheres;
-    uint32_t n_lights = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const rt_sphere& sp = s->spheres[i];
-        if (sp.kind > RT_LIGHT) return fail(RT_ERR_INVALID, "unknown material kind");
-        if (sp.kind == RT_LIGHT) ++n_lights;
-        if (sp.kind == RT_TEXTURE) {
-            if (sp.texture < 0 || (uint64_t)sp.texture >= s->n_textures) return fail(RT_ERR_INVALID, "texture index out of range");
-            const rt_image& im = s->textures[sp.texture];
-            if (!im.rgb8 || im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "empty texture image");
-        }
-    }
-    if (n_lights >= 10) return fail(RT_ERR_UNSUPPORTED, "10 or more lights: the reference's light recursion (raytracer.rs:99-114) does not terminate when n_lights * 0.1 >= 1");
-    if (n_lights > 0 && opts.variant == RT_VARIANT_LANES) return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES has no light support");
-    if (s->sky.mode > RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "unknown sky mode");
-    if (s->sky.mode == RT_SKY_TEXTURE && (!s->sky.tex.rgb8 || s->sky.tex.width == 0 || s->sky.tex.height == 0))
-        return fail(RT_ERR_INVALID, "sky texture is empty");
-
-    DeviceCtx* ctx = nullptr;
-    int rc = get_ctx(opts.device, &ctx);
-    if (rc != RT_OK) return rc;
-
-    rtb200_scene_t* h = new rtb200_scene_t();
-    h->device = ctx->device; h->ctx = ctx; h->opts = opts;
-    h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
-    h->lanes = (opts.variant == RT_VARIANT_LANES);
-    if (opts.variant > RT_VARIANT_BRUTE_FORCE) return fail(RT_ERR_INVALID, "unknown variant");
-    struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
-
-    // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
+// Host-side construction of every array the closest-hit stage reads (no CUDA calls): recentring offset, first-level filter
+// records (cluster bounds, or the spheres themselves), second-level records + slot map + |c| of the bounds, exact geometry
+// and materials. Kept separate from the upload so that CPU tests can check the soundness of the records
+// (rtb200_debug_filter_records, tests/test_filter_records_cpu.py).
+struct FilterRecords {
     double g[3] = {0, 0, 0};
+    bool two_level = false;
+    uint32_t n_pairs = 0, n_clusters = 0;
+    std::vector<float> first;     // n_pairs * 8 floats, pair-packed {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}
+    std::vector<float> sfilt;     // n_clusters * kClusterK * 4 floats
+    std::vector<uint16_t> orig;   // n_clusters * kClusterK
+    std::vector<float> cmeta;     // n_clusters
+    std::vector<double> geo;      // n * 4
+    std::vector<DevMat> mat;      // n
+};
+
+static void build_filter_records(const rt_scene* s, bool allow_two_level, FilterRecords& R) {
+    const uint32_t n = (uint32_t)s->n_spheres;
+    double g[3] = {0, 0, 0};
+    // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
     if (n) {
         std::vector<double> tmp(n);
         for (int c = 0; c < 3; ++c) {
@@ -315,9 +215,8 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         rec[3] = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
         if (!(std::isfinite(rec[0]) && std::isfinite(rec[1]) && std::isfinite(rec[2])) || !(c2 < 1e30)) { rec[0] = rec[1] = rec[2] = 0.f; rec[3] = INFINITY; }
     };
-    bool two_level = n > 32 && !h->lanes && !h->exact;
+    bool two_level = n > 32 && allow_two_level;
     if (const char* e2 = getenv("RTB200_TWO_LEVEL")) two_level = two_level && atoi(e2) != 0;
-    if (opts.variant == RT_VARIANT_BRUTE_FORCE) two_level = false;
     std::vector<float> cfilt, sfilt;
     std::vector<uint16_t> orig;
     std::vector<float> cmeta;
@@ -403,6 +302,163 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         }
     }
 
+    R.g[0] = g[0]; R.g[1] = g[1]; R.g[2] = g[2];
+    R.two_level = two_level;
+    R.n_clusters = n_clusters;
+    R.n_pairs = two_level ? n_cpairs : n_pairs;
+    R.first = two_level ? std::move(cfilt) : std::move(filt);
+    R.sfilt = std::move(sfilt); R.orig = std::move(orig); R.cmeta = std::move(cmeta);
+    R.geo = std::move(geo); R.mat = std::move(mat);
+}
+
+extern "C" {
+
+int rtb200_abi_version(void) { return RTB200_ABI_VERSION; }
+const char* rtb200_last_error(void) { return g_last_error.c_str(); }
+
+// Camera::new — camera.rs:45-77. Host, once per frame, f64, same operation order as the reference.
+// (Compiled with -fmad=false / no host contraction: see the Makefile.)
+int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out) {
+    if (!p || !out) return fail(RT_ERR_INVALID, "null argument");
+    const double PI = 3.14159265358979323846264338327950288;
+    double theta = p->vfov_deg * (PI / 180.0);
+    double half_height = std::tan(theta / 2.0);
+    double half_width = p->aspect * half_height;
+    V3 look_from = v3(p->look_from), look_at = v3(p->look_at), vup = v3(p->vup);
+    V3 w = vunit(look_from - look_at);
+    V3 u = vunit(vcross(vup, w));
+    V3 v = vcross(w, u);
+    V3 origin = look_from;
+    V3 llc = origin - (u * half_width) - (v * half_height) - w;
+    V3 horizontal = u * 2.0 * half_width;
+    V3 vertical = v * 2.0 * half_height;
+    out->origin = rv(origin); out->lower_left_corner = rv(llc); out->horizontal = rv(horizontal); out->vertical = rv(vertical);
+    return RT_OK;
+}
+
+uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_t band_rows) {
+    if (world <= 1) return height;
+    if (band_rows == 0) band_rows = 1;
+    uint32_t rows = 0;
+    for (uint32_t y = 0; y < height; ++y)
+        if ((int32_t)((y / band_rows) % (uint32_t)world) == rank) ++rows;
+    return rows;
+}
+
+static int render_collect(rtb200_scene_handle h, rt_stats* stats);
+
+// Diagnostic (host only, no GPU needed): the filter records rtb200_scene_upload would stage for `scene`.
+// info = {two_level, n_first_level_pairs, n_clusters, cluster_size}; arrays are filled up to their capacities (in elements).
+int rtb200_debug_filter_records(const rt_scene* s, uint32_t variant, double recentre[3], uint32_t info[4],
+                                float* first, uint64_t cap_first, float* second, uint64_t cap_second,
+                                uint16_t* slot_to_sphere, uint64_t cap_slots, float* cluster_abs, uint64_t cap_clusters) {
+    if (!s || !info) return fail(RT_ERR_INVALID, "null argument");
+    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
+    FilterRecords R;
+    build_filter_records(s, variant != RT_VARIANT_BRUTE_FORCE && variant != RT_VARIANT_LANES && variant != RT_VARIANT_EXACT_F64, R);
+    if (recentre) { recentre[0] = R.g[0]; recentre[1] = R.g[1]; recentre[2] = R.g[2]; }
+    info[0] = R.two_level ? 1u : 0u; info[1] = R.n_pairs; info[2] = R.n_clusters; info[3] = (uint32_t)kClusterK;
+    if (first) memcpy(first, R.first.data(), std::min<uint64_t>(cap_first, R.first.size()) * 4);
+    if (second) memcpy(second, R.sfilt.data(), std::min<uint64_t>(cap_second, R.sfilt.size()) * 4);
+    if (slot_to_sphere) memcpy(slot_to_sphere, R.orig.data(), std::min<uint64_t>(cap_slots, R.orig.size()) * 2);
+    if (cluster_abs) memcpy(cluster_abs, R.cmeta.data(), std::min<uint64_t>(cap_clusters, R.cmeta.size()) * 4);
+    return RT_OK;
+}
+
+int rtb200_scene_release(rtb200_scene_handle h) {
+    if (!h) return RT_OK;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return RT_OK;
+}
+
+// Scene arrays are collected first and then placed in ONE device arena filled by ONE host->device copy
+// (a per-frame upload costs one cudaMalloc, one copy, one cudaFree). `field` is patched with the device address.
+static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** field) {
+    *field = nullptr;
+    if (bytes == 0) bytes = 16;
+    h->uploads.push_back(rtb200_scene_t::Upload{src, bytes, field});
+    return RT_OK;
+}
+
+static int commit_uploads(rtb200_scene_t* h) {
+    size_t total = 0;
+    for (auto& u : h->uploads) total += (u.bytes + 255) & ~(size_t)255;
+    void* base = nullptr;
+    CU(cudaMalloc(&base, total ? total : 256));
+    h->owned.push_back(base);
+    size_t off = 0;
+    for (auto& u : h->uploads) { *u.field = (char*)base + off; off += (u.bytes + 255) & ~(size_t)255; }   // addresses first: tables may hold them
+    h->staging.assign(total, 0);
+    off = 0;
+    for (auto& u : h->uploads) {
+        if (u.src) { memcpy(h->staging.data() + off, u.src, u.bytes); h->h2d_bytes += u.bytes; }
+        off += (u.bytes + 255) & ~(size_t)255;
+    }
+    if (total) CU(cudaMemcpyAsync(base, h->staging.data(), total, cudaMemcpyHostToDevice, h->ctx->stream));
+    h->uploads.clear();
+    return RT_OK;
+}
+
+int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
+    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rt_options opts{};
+    opts.device = -1; opts.rank = 0; opts.world = 1; opts.band_rows = 1; opts.variant = RT_VARIANT_AUTO;
+    if (opts_in) opts = *opts_in;
+    if (opts.world <= 0) opts.world = 1;
+    if (opts.band_rows == 0) opts.band_rows = 1;
+    if (opts.rank < 0 || opts.rank >= opts.world) return fail(RT_ERR_INVALID, "rank outside [0, world)");
+    if (opts.flags != 0) return fail(RT_ERR_INVALID, "flags must be 0");
+    if (s->width < 2 || s->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by w-1, h-1: raytracer.rs:199-200)");
+    if (s->samples_per_pixel == 0) return fail(RT_ERR_INVALID, "samples_per_pixel must be > 0");
+    if ((uint64_t)s->width * s->height >= (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
+    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
+    if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
+
+    uint32_t n = (uint32_t)s->n_spheres;
+    uint32_t n_lights = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const rt_sphere& sp = s->spheres[i];
+        if (sp.kind > RT_LIGHT) return fail(RT_ERR_INVALID, "unknown material kind");
+        if (sp.kind == RT_LIGHT) ++n_lights;
+        if (sp.kind == RT_TEXTURE) {
+            if (sp.texture < 0 || (uint64_t)sp.texture >= s->n_textures) return fail(RT_ERR_INVALID, "texture index out of range");
+            const rt_image& im = s->textures[sp.texture];
+            if (!im.rgb8 || im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "empty texture image");
+        }
+    }
+    if (n_lights >= 10) return fail(RT_ERR_UNSUPPORTED, "10 or more lights: the reference's light recursion (raytracer.rs:99-114) does not terminate when n_lights * 0.1 >= 1");
+    if (n_lights > 0 && opts.variant == RT_VARIANT_LANES) return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES has no light support");
+    if (s->sky.mode > RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "unknown sky mode");
+    if (s->sky.mode == RT_SKY_TEXTURE && (!s->sky.tex.rgb8 || s->sky.tex.width == 0 || s->sky.tex.height == 0))
+        return fail(RT_ERR_INVALID, "sky texture is empty");
+
+    DeviceCtx* ctx = nullptr;
+    int rc = get_ctx(opts.device, &ctx);
+    if (rc != RT_OK) return rc;
+
+    rtb200_scene_t* h = new rtb200_scene_t();
+    h->device = ctx->device; h->ctx = ctx; h->opts = opts;
+    h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
+    h->lanes = (opts.variant == RT_VARIANT_LANES);
+    if (opts.variant > RT_VARIANT_BRUTE_FORCE) return fail(RT_ERR_INVALID, "unknown variant");
+    struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
+
+    FilterRecords R;
+    build_filter_records(s, !h->lanes && !h->exact && opts.variant != RT_VARIANT_BRUTE_FORCE, R);
+    const bool two_level = R.two_level;
+    const uint32_t n_clusters = R.n_clusters;
+    uint32_t n_pairs = R.n_pairs;
+    const double* g = R.g;
+    std::vector<float>& filt = R.first; std::vector<float>& cfilt = R.first;
+    std::vector<float>& sfilt = R.sfilt; std::vector<uint16_t>& orig = R.orig; std::vector<float>& cmeta = R.cmeta;
+    std::vector<double>& geo = R.geo; std::vector<DevMat>& mat = R.mat;
+    const double U = 5.9604644775390625e-8;   // 2^-24
+    (void)n_clusters;
+
     TraceParams& tp = h->tp;
     void* d = nullptr;
     tp.two_level = two_level ? 1u : 0u;
@@ -412,7 +468,6 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         if ((rc = upload_array(h, sfilt.data(), sfilt.size() * 4, (void**)&tp.sfilt)) != RT_OK) return rc;
         if ((rc = upload_array(h, orig.data(), orig.size() * 2, (void**)&tp.orig)) != RT_OK) return rc;
         if ((rc = upload_array(h, cmeta.data(), cmeta.size() * 4, (void**)&tp.cmeta)) != RT_OK) return rc;
-        n_pairs = n_cpairs;    // the first-level scan loop runs over the cluster records
     } else {
         if ((rc = upload_array(h, filt.data(), filt.size() * 4, (void**)&tp.filt)) != RT_OK) return rc;
         tp.sfilt = nullptr; tp.orig = nullptr; tp.cmeta = nullptr;

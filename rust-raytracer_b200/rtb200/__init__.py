@@ -93,6 +93,7 @@ ABI_SYMBOLS = [
     "rtb200_scene_release", "rtb200_probe_sphere_hit", "rtb200_probe_refract", "rtb200_probe_reflectance",
     "rtb200_probe_sky", "rtb200_probe_get_ray", "rtb200_probe_rng", "rtb200_probe_quantise",
     "rtb200_decode_jpeg_file", "rtb200_free", "rtb200_render_device_async", "rtb200_render_device_wait",
+    "rtb200_debug_filter_records",
 ]
 
 _lib = None
@@ -130,6 +131,8 @@ def lib() -> C.CDLL:
     L.rtb200_decode_jpeg_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rtb200_free.argtypes = [C.c_void_p]
     L.rtb200_free.restype = None
+    L.rtb200_debug_filter_records.argtypes = [C.POINTER(rt_scene), C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64,
+                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     _lib = L
     return L
 
@@ -300,6 +303,21 @@ def load_scene(path: str, base_dir: Optional[str] = None) -> Scene:
         if not os.path.isdir(os.path.join(base_dir, "data")):
             base_dir = os.path.dirname(base_dir)
     return Scene.from_config(cfg, base_dir)
+
+
+def filter_records(scene: "Scene", variant: int = RT_VARIANT_AUTO) -> dict:
+    """Host-side diagnostic: the conservative filter records of the closest-hit stage (no GPU needed)."""
+    n = scene.n_spheres
+    cap_c = 2 * n + 64
+    first = np.zeros(8 * (cap_c + 16), np.float32); second = np.zeros(4 * 8 * cap_c, np.float32)
+    slots = np.zeros(8 * cap_c, np.uint16); cabs = np.zeros(cap_c, np.float32)
+    g = (C.c_double * 3)(); info = (C.c_uint32 * 4)()
+    _check(lib().rtb200_debug_filter_records(C.byref(scene.c), variant, g, info, first.ctypes.data, first.size, second.ctypes.data, second.size,
+                                             slots.ctypes.data, slots.size, cabs.ctypes.data, cabs.size))
+    two, n_pairs, n_clusters, k = (int(x) for x in info)
+    return {"two_level": bool(two), "n_pairs": n_pairs, "n_clusters": n_clusters, "cluster_size": k, "recentre": np.array(g[:]),
+            "first": first[: n_pairs * 8].reshape(n_pairs, 2, 4), "second": second[: n_clusters * k * 4].reshape(n_clusters, k // 2, 2, 4),
+            "slot_to_sphere": slots[: n_clusters * k].reshape(n_clusters, k), "cluster_abs": cabs[:n_clusters]}
 
 
 def make_options(device: int = -1, rank: int = 0, world: int = 1, band_rows: int = 1, variant: int = RT_VARIANT_AUTO,
