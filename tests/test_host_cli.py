@@ -13,6 +13,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(REPO, "rust-raytracer_b200", "raytracer")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _cli_built():
+    """The CLI is a build artefact (git-ignored); __graft_entry__.build() makes it, a bare checkout may not have it yet."""
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.join(REPO, "rust-raytracer_b200"), "raytracer"])
+
+
 def _run(args, **kw):
     return subprocess.run([CLI] + args, capture_output=True, text=True, timeout=300, **kw)
 
