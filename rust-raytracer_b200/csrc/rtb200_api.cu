@@ -516,7 +516,7 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
         else if (filt_smem <= half_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; }
         else if (full_smem <= per_cta_budget) { tp.scene_in_smem = 1; h->smem = full_smem; ctas_per_sm = 1; }
         else if (filt_smem <= per_cta_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; ctas_per_sm = 1; }
-        else return fail(RT_ERR_UNSUPPORTED, "sphere filter records exceed shared memory (streaming tiles not built yet)");
+        else return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES: the sphere filter records exceed shared memory (use the default variant, which culls through cluster bounds)");
         h->grid = ctx->sm_count * ctas_per_sm;
     } else {
         // What goes to shared memory besides the first-level filter records and the ray pool, in order of value:

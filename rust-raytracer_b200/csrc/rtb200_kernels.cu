@@ -1,19 +1,12 @@
-// rtb200_kernels.cu — sm_100a kernels of the render path.
+// rtb200_kernels.cu — the resolve kernel, the device-routine probes, and the earlier lane-autonomous trace kernel.
 //
-// rt_trace_kernel: persistent-threads wavefront tracer. Every CTA stages the scene's sphere records into
-// shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier), then its warps loop over three
-// warp-synchronous stages until the sample queue is drained:
-//   ray-gen      dead lanes are found with a warp ballot, a single warp-aggregated atomic pops that many
-//                (pixel,sample) work items from the global queue, and the lanes generate primary rays
-//                (render_line's jitter + Camera::get_ray, raytracer.rs:199-201, camera.rs:79-84);
-//   closest-hit  hit_world (raytracer.rs:44-59) over ALL spheres, as a conservative f32 filter (7 FFMA per
-//                sphere, two spheres per packed FFMA2) that appends candidates to a per-lane list, followed by
-//                the reference-exact f64 Sphere::hit (sphere.rs:46-78) on the candidates only;
-//   shade        Material::scatter (materials.rs:44-54) / sky (raytracer.rs:134-163), iterative instead of
-//                recursive: albedo codes go to a per-lane stack that is unwound backwards on termination so the
-//                f32 products associate exactly like the reference's recursion (raytracer.rs:117-122).
-// Finished samples are written to a [sample][pixel] staging buffer; rt_resolve_kernel then adds them per pixel in
-// sample order (raytracer.rs:203-205) and applies sqrt + u8 quantisation (raytracer.rs:207-216).
+// rt_resolve_kernel: adds each pixel's samples in sample order (raytracer.rs:203-205), then scale*sum, sqrt and the u8
+// quantisation (raytracer.rs:207-216). Used after every trace launch of the production kernel (rtb200_wavefront.cu).
+//
+// rt_trace_kernel (RT_VARIANT_LANES, kept for comparison and as a second implementation in the parity tests): every lane
+// owns one path and refills itself from the global (pixel,sample) queue; same scene staging by TMA bulk copies, same
+// single-level f32 filter + exact f64 confirmation, same albedo stack, no CTA-level sorting, no lights. It was the
+// first measured kernel of round 1; the production kernel is rt_wavefront_kernel.
 #include "rtb200_kernels.cuh"
 
 using namespace rtd;
