@@ -6,7 +6,7 @@
 // rt_trace_kernel (RT_VARIANT_LANES, kept for comparison and as a second implementation in the parity tests): every lane
 // owns one path and refills itself from the global (pixel,sample) queue; same scene staging by TMA bulk copies, same
 // single-level f32 filter + exact f64 confirmation, same albedo stack, no CTA-level sorting, no lights. It was the
-// first measured kernel of round 1 (DESIGN.md §4.4); the production kernel is rt_wavefront_kernel.
+// first measured kernel of round 1 (DESIGN.md §4.5); the production kernel is rt_wavefront_kernel.
 #include "rtb200_kernels.cuh"
 
 using namespace rtd;
