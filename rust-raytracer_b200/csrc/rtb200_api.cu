@@ -119,6 +119,7 @@ struct rtb200_scene_t {
     bool exact = false;
     bool lanes = false;
     int block = 256;
+    int minb = 4;
     int grid = 0;
     size_t smem = 0;
     uint32_t spp_batch = 0;
@@ -521,25 +522,28 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     } else {
         // What goes to shared memory besides the first-level filter records and the ray pool, in order of value:
         // second-level sphere records (two-level mode), exact geometry (read by every f64 confirmation), materials
-        // (read once per hit). Pick the richest set that still leaves kWfThreadsPerSm threads resident per SM.
+        // (read once per hit). Pick the richest set that still leaves the targeted number of CTAs resident per SM.
         // RTB200_WF_SMEM=<mask> overrides (bit0 sfilt, bit1 geo, bit2 mat) for tuning experiments.
         const char* es = getenv("RTB200_WF_SMEM");
         const uint32_t masks[] = {7u, 3u, 1u, 0u};
         bool found = false;
-        const int want = kWfThreadsPerSm / 256;
-        for (int pass = 0; pass < 2 && !found; ++pass) {
-            for (uint32_t mask : masks) {
-                if (es && (uint32_t)atoi(es) != mask) continue;
-                if (!two_level && (mask & 1u) && mask != 7u) continue;            // bit0 is meaningless without a second level
-                size_t sm = wavefront_smem_bytes(n, n_pairs, n_clusters, two_level, mask, 256);
-                if (sm > ctx->max_smem) continue;
-                int occ = wavefront_max_ctas_per_sm(sm, 256);
-                if (occ <= 0) continue;
-                if (pass == 0 && occ < want) continue;                             // first pass: insist on full residency
-                h->block = 256; h->smem = sm; tp.scene_in_smem = mask; h->grid = ctx->sm_count * occ;
-                found = true;
-                break;
+        // first choice: four resident CTAs per SM (kernel built for 64 registers); else the 128-register build at whatever fits
+        for (int minb : {4, 2}) {
+            for (int need : {minb, 1}) {
+                for (uint32_t mask : masks) {
+                    if (found) break;
+                    if (es && (uint32_t)atoi(es) != mask) continue;
+                    if (!two_level && (mask & 1u) && mask != 7u) continue;            // bit0 is meaningless without a second level
+                    size_t sm = wavefront_smem_bytes(n, n_pairs, n_clusters, two_level, mask, 256);
+                    if (sm > ctx->max_smem) continue;
+                    int occ = wavefront_max_ctas_per_sm(sm, minb);
+                    if (occ < need || occ <= 0) continue;
+                    h->block = 256; h->minb = minb; h->smem = sm; tp.scene_in_smem = mask; h->grid = ctx->sm_count * occ;
+                    found = true;
+                }
+                if (minb == 4) break;   // the 64-register build is only worth it at full residency
             }
+            if (found) break;
         }
         if (!found) return fail(RT_ERR_UNSUPPORTED, "first-level filter records exceed shared memory (needs a third level / streaming tiles)");
     }
@@ -619,7 +623,7 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
         } else if (h->lanes) {
             CU(launch_trace(tp, h->grid, h->smem, false, st));
         } else {
-            CU(launch_wavefront(tp, h->grid, h->smem, h->block, h->exact, st));
+            CU(launch_wavefront(tp, h->grid, h->smem, h->minb, h->exact, st));
         }
         CU(cudaEventRecord(fev[3 + 2 * b], st));
         ResolveParams q{};

@@ -141,6 +141,30 @@ RT_DEV bool sphere_root(D3 center, double radius, D3 o, D3 d, double a, double t
     return false;
 }
 
+// Two spheres at once: the same operations in the same order per sphere, with the two dependent f64 chains interleaved
+// (the confirmation stage is latency-bound). Root selection as in sphere_root with t_max = +max.
+RT_DEV void sphere_root2(D3 c0, double r0, D3 c1, double r1, D3 o, D3 d, double a, double t_min, bool& h0, double& root0, bool& h1, double& root1) {
+    D3 oc0 = sub(o, c0), oc1 = sub(o, c1);
+    double hb0 = dot(oc0, d), hb1 = dot(oc1, d);
+    double cc0 = __dsub_rn(length_squared(oc0), __dmul_rn(r0, r0)), cc1 = __dsub_rn(length_squared(oc1), __dmul_rn(r1, r1));
+    double disc0 = __dsub_rn(__dmul_rn(hb0, hb0), __dmul_rn(a, cc0)), disc1 = __dsub_rn(__dmul_rn(hb1, hb1), __dmul_rn(a, cc1));
+    h0 = false; h1 = false;
+    if (disc0 >= 0.0 || disc1 >= 0.0) {
+        // sqrt/div of a negative discriminant give NaN, which fails every comparison below
+        double sq0 = __dsqrt_rn(disc0), sq1 = __dsqrt_rn(disc1);
+        double ra0 = __ddiv_rn(__dsub_rn(-hb0, sq0), a), ra1 = __ddiv_rn(__dsub_rn(-hb1, sq1), a);
+        double rb0 = __ddiv_rn(__dadd_rn(-hb0, sq0), a), rb1 = __ddiv_rn(__dadd_rn(-hb1, sq1), a);
+        if (disc0 >= 0.0) {
+            if (ra0 < DBL_MAX && ra0 > t_min) { root0 = ra0; h0 = true; }
+            else if (rb0 < DBL_MAX && rb0 > t_min) { root0 = rb0; h0 = true; }
+        }
+        if (disc1 >= 0.0) {
+            if (ra1 < DBL_MAX && ra1 > t_min) { root1 = ra1; h1 = true; }
+            else if (rb1 < DBL_MAX && rb1 > t_min) { root1 = rb1; h1 = true; }
+        }
+    }
+}
+
 struct HitRec { D3 point, normal; bool front_face; };
 // The rest of sphere.rs:59-76 for the accepted root: p = ray.at(t), normal = (p - c)/r, front-face flip.
 RT_DEV HitRec hit_record(D3 center, double radius, D3 o, D3 d, double t) {

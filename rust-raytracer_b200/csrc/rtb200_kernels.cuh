@@ -10,10 +10,6 @@ namespace rtk {
 
 constexpr int kBlock = 256;        // threads per CTA of the trace kernel
 constexpr int kCtasPerSm = 2;        // lane-autonomous kernel (rt_trace_kernel)
-#ifndef RT_WF_THREADS
-#define RT_WF_THREADS 768
-#endif
-constexpr int kWfThreadsPerSm = RT_WF_THREADS;  // CTA-wavefront kernel (rt_wavefront_kernel): resident threads per SM the register budget targets
 constexpr int kMaxCand = 24;       // per-lane candidate slots in shared memory (lanes kernel)
 #ifndef RT_CLUSTER_K
 #define RT_CLUSTER_K 4
@@ -93,8 +89,8 @@ struct ResolveParams {
 size_t trace_smem_bytes(uint32_t n, uint32_t n_pairs, bool scene_in_smem);
 cudaError_t launch_trace(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st);
 size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t smem_mask, int block);
-cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st);
-int wavefront_max_ctas_per_sm(size_t smem, int block);
+cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int minb, bool exact, cudaStream_t st);
+int wavefront_max_ctas_per_sm(size_t smem, int minb);
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t st);
 cudaError_t trace_configure(int device, int* sm_count, size_t* max_smem_optin);
 

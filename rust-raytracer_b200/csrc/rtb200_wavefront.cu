@@ -28,6 +28,9 @@ using namespace rtd;
 #ifndef RT_SAMPLE_ILP
 #define RT_SAMPLE_ILP 1   // two rejection trials per trip with their Philox blocks computed together (bit-identical stream)
 #endif
+#ifndef RT_CONFIRM_ILP
+#define RT_CONFIRM_ILP 0   // two candidates per trip with interleaved f64 chains: bit-identical, but measured 5 % SLOWER (wasted sqrt/div on misses)
+#endif
 #ifndef RT_SMEM_STACK
 #define RT_SMEM_STACK 3   // albedo-stack levels kept in shared memory per slot (deeper levels live in global memory)
 #endif
@@ -103,8 +106,8 @@ size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, b
     return wf_layout(n, n_pairs, n_clusters, two_level, smem_mask, (uint32_t)block).total;
 }
 
-template <int kBlock, bool EXACT, bool LIGHTS, bool TWO>
-__global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
+template <int kBlock, int MINB, bool EXACT, bool LIGHTS, bool TWO>
+__global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WfSmem L = wf_layout(p.n, p.n_pairs, p.n_clusters, TWO, p.scene_in_smem, kBlock);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -243,6 +246,25 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                 }
                 ++st_cand;
             };
+            auto consider = [&](int j, bool hit, double root) {
+                if (hit && (best < 0 || root < best_t || (root == best_t && j < best))) { best_t = root; best = j; }
+            };
+            // the candidates of a list, two at a time (interleaved f64 chains), then the odd one
+            auto confirm_list = [&](const uint16_t* cl, int cnt) {
+                int j = 0;
+                if (RT_CONFIRM_ILP) {
+                    for (; j + 1 < cnt; j += 2) {
+                        const int j0 = (int)cl[j * kBlock + tid], j1 = (int)cl[(j + 1) * kBlock + tid];
+                        if (j0 >= (int)p.n || j1 >= (int)p.n) { confirm(j0); confirm(j1); continue; }   // padding record in the pair
+                        const double4 g0 = geo[j0], g1 = geo[j1];
+                        bool h0, h1; double r0 = 0.0, r1 = 0.0;
+                        sphere_root2(mk(g0.x, g0.y, g0.z), g0.w, mk(g1.x, g1.y, g1.z), g1.w, o, d, a, 0.001, h0, r0, h1, r1);
+                        consider(j0, h0, r0); consider(j1, h1, r1);
+                        st_cand += 2;
+                    }
+                }
+                for (; j < cnt; ++j) confirm((int)cl[j * kBlock + tid]);
+            };
             const bool warp_has_ray = __ballot_sync(FULL, alive) != 0u;   // a warp whose 32 slots are all empty skips the scan (frame tail)
             if (!EXACT && warp_has_ray) {
                 // per-ray filter constants in the recentred f32 frame (DESIGN.md "filter soundness")
@@ -356,14 +378,14 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
                             }
                             // ---- exact f64 confirmation of the listed spheres ----
                             const int n2 = (int)((l2_addr - l2_base) / (kBlock * 2u));
-                            for (int j = 0; j < n2; ++j) confirm((int)s_l2[j * kBlock + tid]);
+                            confirm_list(s_l2, n2);
                             l2_addr = l2_base;
                             if (k >= n1) break;
                         }
                         l1_addr = l1_base;
                     } else {
                         const int n1 = (int)((l1_addr - l1_base) / (kBlock * 2u));
-                        for (int j = 0; j < n1; ++j) confirm((int)s_l1[j * kBlock + tid]);
+                        confirm_list(s_l1, n1);
                         l1_addr = l1_base;
                     }
                     if (pp >= np) break;
@@ -614,29 +636,40 @@ __global__ void __launch_bounds__(kBlock, kWfThreadsPerSm / kBlock) rt_wavefront
     }
 }
 
-template <int B, bool E, bool LI, bool TW>
+// MINB = CTAs per SM the register allocation targets: 4 (64 registers, small spills) when shared memory lets four pools be
+// resident, else 2 (up to 128 registers, no spills) - e.g. when 10 k spheres' first-level records take 40 KB per CTA.
+template <int MB, bool E, bool LI, bool TW>
 static cudaError_t launch_wf(const TraceParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<B, E, LI, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<256, MB, E, LI, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rt_wavefront_kernel<B, E, LI, TW><<<grid, B, smem, st>>>(p);
+    rt_wavefront_kernel<256, MB, E, LI, TW><<<grid, 256, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int block, bool exact, cudaStream_t st) {
-    (void)block;
+template <int MB>
+static cudaError_t launch_wf_minb(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st) {
     const bool li = p.n_lights > 0, tw = p.two_level != 0;
     if (exact) {   // every sphere in f64: the filter levels are not used at all
-        return li ? launch_wf<256, true, true, false>(p, grid, smem, st) : launch_wf<256, true, false, false>(p, grid, smem, st);
+        return li ? launch_wf<MB, true, true, false>(p, grid, smem, st) : launch_wf<MB, true, false, false>(p, grid, smem, st);
     }
-    if (tw) return li ? launch_wf<256, false, true, true>(p, grid, smem, st) : launch_wf<256, false, false, true>(p, grid, smem, st);
-    return li ? launch_wf<256, false, true, false>(p, grid, smem, st) : launch_wf<256, false, false, false>(p, grid, smem, st);
+    if (tw) return li ? launch_wf<MB, false, true, true>(p, grid, smem, st) : launch_wf<MB, false, false, true>(p, grid, smem, st);
+    return li ? launch_wf<MB, false, true, false>(p, grid, smem, st) : launch_wf<MB, false, false, false>(p, grid, smem, st);
 }
 
-int wavefront_max_ctas_per_sm(size_t smem, int block) {
-    (void)block;
+cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int minb, bool exact, cudaStream_t st) {
+    return minb >= 4 ? launch_wf_minb<4>(p, grid, smem, exact, st) : launch_wf_minb<2>(p, grid, smem, exact, st);
+}
+
+int wavefront_max_ctas_per_sm(size_t smem, int minb) {
     int nb = 0;
-    cudaFuncSetAttribute(rt_wavefront_kernel<256, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, false, true, true>, 256, smem);
+    cudaError_t e;
+    if (minb >= 4) {
+        cudaFuncSetAttribute(rt_wavefront_kernel<256, 4, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, 4, false, true, true>, 256, smem);
+    } else {
+        cudaFuncSetAttribute(rt_wavefront_kernel<256, 2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, 2, false, true, true>, 256, smem);
+    }
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
 }
