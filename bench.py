@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time of the cpu_baseline sample of the GPU arm")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: CPU seconds for all warmup+steps renders")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -99,33 +100,96 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_leg(cfg_name: str, target_seconds: float):
-    """Times the CPU oracle (C++ restatement of the reference's rayon row loop, all host threads) on a bounded
-    sample of the workload: the same scene and image size at reduced samples-per-pixel (Mrays/s does not depend on
-    spp). Only place besides tests/ and smoke() where oracle/ is executed."""
+WORKLOADS = {
+    "C1": "reference data/test_scene.json objects", "C2": "reference data/cover_scene.json objects",
+    "C3": "reference data/cover_scene.json objects", "C5": "reference data/cover_scene.json objects",
+    "C4": "RTIOW random scene on a 100x100 grid (seeded restatement of config.rs:149-226)",
+}
+
+
+def workload_string(cfg_name: str, cfg: dict) -> str:
+    """The SAME string in both arms (the driver compares them)."""
+    base = cfg_name.upper().rstrip("SM")
+    return (f"{cfg_name}: {WORKLOADS.get(base, base)} ({len(cfg['objects'])} spheres) {cfg['width']}x{cfg['height']} "
+            f"{cfg['samples_per_pixel']}spp depth {cfg['max_depth']}, gradient sky, seed 0x5EED")
+
+
+def host_threads():
+    """(hardware threads, physical cores) this process may run on."""
+    aff = sorted(os.sched_getaffinity(0))
+    cores = set()
+    for c in aff:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        except OSError:
+            cores.add(str(c))
+    return len(aff), max(1, len(cores))
+
+
+CPU_ARM_ENV = "RTB200_CPU_ARM_ENV"
+
+
+def cpu_arm_env() -> dict:
+    """Environment of the CPU arm: explicit thread count (torchrun exports OMP_NUM_THREADS=1), threads pinned one per
+    core first, then per hardware thread. Must be in place BEFORE libgomp is loaded, hence the re-exec / subprocess."""
+    n_threads, _ = host_threads()
+    env = dict(os.environ)
+    env.update({"OMP_NUM_THREADS": str(n_threads), "OMP_PROC_BIND": "spread", "OMP_PLACES": "cores", "OMP_DYNAMIC": "false",
+                CPU_ARM_ENV: "1"})
+    return env
+
+
+def _cpu_scene(cfg: dict):
+    """Scene for the CPU arm without mapping librtb200.so: Camera::new comes from the oracle."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import oracle_py as O
+    import rtb200 as R
     from rtb200 import scenes
+    R.set_camera_backend(O.lib().oracle_camera_new)
+    return R.Scene.from_config(cfg, scenes.SCENES_DIR), O
 
+
+def cpu_arm(cfg_name: str, steps: int, warmup: int, budget_s: float) -> dict:
+    """The CPU restatement of the reference's rayon row loop (oracle/, OpenMP schedule(dynamic,1) = one task per row) on
+    the box's host cores, on a bounded sample of the workload: same scene, size and depth, samples-per-pixel reduced so
+    that warmup+steps renders fit `budget_s` (full spp when that fits). Mrays/s does not depend on spp. Both thread
+    counts (one per physical core / every hardware thread) are timed during calibration; the faster one runs the steps.
+    Only place besides tests/ and smoke() where oracle/ is executed."""
+    assert os.environ.get(CPU_ARM_ENV) == "1", "cpu_arm must run in the prepared environment (see cpu_arm_env)"
+    from rtb200 import scenes
     cfg = scenes.config(cfg_name)
     full_spp = cfg["samples_per_pixel"]
-    import rtb200 as R
-    cfg1 = dict(cfg); cfg1["samples_per_pixel"] = 1
-    sc = R.Scene.from_config(cfg1, scenes.SCENES_DIR)
-    _, _, st = O.render(sc, linear=False, rgb8=True)          # calibration pass, 1 spp
-    rate = st["rays"] / (st["render_ms"] / 1e3)
-    spp = int(max(1, min(full_spp, round(target_seconds * rate / max(st["rays"], 1)))))
-    cfgs = dict(cfg); cfgs["samples_per_pixel"] = spp
-    sc = R.Scene.from_config(cfgs, scenes.SCENES_DIR)
-    t0 = time.perf_counter()
-    _, _, st = O.render(sc, linear=False, rgb8=True)
-    dt = time.perf_counter() - t0
+    n_threads, n_cores = host_threads()
+    cal_cfg = dict(cfg); cal_cfg["samples_per_pixel"] = 1
+    sc, O = _cpu_scene(cal_cfg)
+    counts = sorted({n_cores, n_threads})
+    rates = {}
+    for _ in range(2):                         # second pass: caches and the OpenMP pool are warm
+        for t in counts:
+            _, _, st = O.render(sc, linear=False, rgb8=True, threads=t)
+            rates[t] = max(rates.get(t, 0.0), st["rays"] / (st["render_ms"] / 1e3))
+    threads = max(rates, key=rates.get)
+    rays_per_spp = st["rays"]
+    per_step = budget_s / max(steps + warmup, 1)
+    spp = int(max(1, min(full_spp, per_step * rates[threads] / max(rays_per_spp, 1))))
+    run_cfg = dict(cfg); run_cfg["samples_per_pixel"] = spp
+    sc, O = _cpu_scene(run_cfg)
+    for _ in range(warmup):
+        O.render(sc, linear=False, rgb8=True, threads=threads)
+    rays = 0; secs = 0.0
+    for _ in range(steps):
+        _, _, st = O.render(sc, linear=False, rgb8=True, threads=threads)
+        assert st["threads"] == threads
+        rays += st["rays"]; secs += st["render_ms"] / 1e3
+    value = rays / secs / 1e6
+    cal = ", ".join(f"{t} threads {rates[t] / 1e6:.1f}" for t in counts)
     return {
-        "value": st["rays"] / (st["render_ms"] / 1e3) / 1e6, "unit": "Mrays/s", "cores": st["threads"], "kind": "port",
-        "sample": f"{cfg_name} scene {cfg['width']}x{cfg['height']} depth {cfg['max_depth']} at {spp} of {full_spp} spp "
-                  f"({st['rays']} rays, {st['render_ms'] / 1e3:.1f} s; C++ restatement of the reference rayon row loop, "
-                  f"OpenMP schedule(dynamic,1), g++ -O3 -ffp-contract=off)",
-        "rays": st["rays"], "seconds": st["render_ms"] / 1e3, "wall_seconds": dt, "spp": spp,
+        "value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "rays": rays, "seconds": secs, "spp": spp, "steps": steps,
+        "sample": f"{workload_string(cfg_name, cfg)}: each step renders {spp} of {full_spp} spp ({rays // max(steps, 1)} rays, {secs / max(steps, 1):.1f} s/step, "
+                  f"{steps} steps); C++ restatement of the reference rayon row loop (OpenMP schedule(dynamic,1), g++ -O3 -ffp-contract=off), "
+                  f"{threads} threads pinned (OMP_PROC_BIND=spread OMP_PLACES=cores) on {n_cores} cores / {n_threads} hardware threads; "
+                  f"calibration at 1 spp, Mrays/s: {cal}",
     }
 
 
@@ -133,28 +197,55 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.environ.get(CPU_ARM_ENV) != "1":     # fresh interpreter: OpenMP reads its environment when libgomp loads
+        os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], cpu_arm_env())
     from rtb200 import scenes
     cfg = scenes.config(args.config)
-    per_step = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
-    legs = []
-    for _ in range(args.warmup):
-        cpu_leg(args.config, per_step / 4)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        legs.append(cpu_leg(args.config, per_step))
-    rays = sum(l["rays"] for l in legs); secs = sum(l["seconds"] for l in legs)
-    value = rays / secs / 1e6
+    r = cpu_arm(args.config, args.steps, args.warmup, args.cpu_budget)
+    value = r["value"]
+    assert r["cores"] > 1 or host_threads()[0] == 1, "CPU arm ran single-threaded"
     line = {
         "impl": "reference", "metric": "Mrays/sec (primary+scattered)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] / max(args.steps, 1) * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: cover_scene objects {cfg['width']}x{cfg['height']} {cfg['samples_per_pixel']}spp depth {cfg['max_depth']}",
-                   "note": "CPU arm; each step renders a bounded sample (reduced spp) of the workload"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": legs[0]["cores"], "kind": "port", "sample": legs[0]["sample"]},
+        "config": {"workload": workload_string(args.config, cfg),
+                   "note": f"CPU arm; each step renders a bounded sample of the workload ({r['spp']} of {cfg['samples_per_pixel']} spp)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    with open("/proc/self/maps") as f:
+        assert "librtb200" not in f.read(), "the CPU arm must not map the product library"
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(cfg_name: str, seconds: float):
+    """cpu_baseline of the GPU arm: the CPU arm in a fresh interpreter (no torch, no librtb200.so, prepared OpenMP env)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", cfg_name, "--steps", "2", "--warmup", "1",
+           "--cpu-budget", str(seconds)]
+    env = cpu_arm_env()
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError(f"cpu arm failed: {out.stderr[-400:]}")
+
+
+def golden_db():
+    p = os.path.join(REPO, "tests", "golden", "frames.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f)
+
+
+def sha256_of(a) -> str:
+    import hashlib
+    import numpy as np
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def run_ours(args):
@@ -266,12 +357,40 @@ def run_ours(args):
         e_total = float(e_rays)
     e2e_value = e_total / e_wall / 1e6
 
+    # ---------------- golden: the timed frame (or, for configs the CPU oracle cannot finish, the same scene at the
+    # committed reduced size rendered by the same N-GPU renderer) against the ORACLE's SHA-256 (tests/golden/frames.json) ----
+    gdb = golden_db()
+    gname = args.config.upper() if args.config.upper() in gdb else (args.config.upper() + "S" if args.config.upper() + "S" in gdb else None)
+    golden = {"status": "none", "case": gname}
+    rays_frame = total_rays / args.steps
+    if gname is not None:
+        if gname == args.config.upper():
+            gframe = rdr.frame.cpu().numpy() if rank == 0 else None
+            grays = rays_frame
+        else:
+            gsc = R.Scene.from_config(scenes.config(gname), scenes.SCENES_DIR)
+            grdr = RD.DistributedRenderer(gsc)
+            gst = grdr.render()
+            torch.cuda.synchronize()
+            gr = torch.tensor([float(gst["rays"])], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(gr, op=dist.ReduceOp.SUM)
+            grays = float(gr[0])
+            gframe = grdr.frame.cpu().numpy() if rank == 0 else None
+            grdr.release()
+        if rank == 0:
+            g = gdb[gname]
+            ok = sha256_of(gframe) == g["sha256_rgb8"] and int(grays) == int(g["rays"])
+            golden = {"status": "match" if ok else "MISMATCH", "case": gname, "what": "sha256 of the RGB8 frame and the ray count vs the CPU oracle (tests/golden/frames.json)",
+                      "rays": int(grays), "rays_oracle": int(g["rays"])}
+
     if rank != 0:
         return
     # frame sanity: what we timed is the real image
     frame = rdr.frame.cpu().numpy()
     assert frame.shape == (h, w, 3) and frame.any()
     assert np.array_equal(frame, host_frame.numpy()), "resident and host-path frames differ"
+    assert golden["status"] != "MISMATCH", f"frame differs from the oracle golden: {golden}"
 
     n = scene.n_spheres
     hbm_peak, peak_src, sm_max = measured_peaks()
@@ -291,7 +410,7 @@ def run_ours(args):
         "metric": "Mrays/sec (primary+scattered)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: reference data/cover_scene.json objects ({n} spheres) {w}x{h} {scene.c.samples_per_pixel}spp depth {scene.c.max_depth}, gradient sky, seed 0x5EED",
+        "config": {"workload": workload_string(args.config, cfg),
                    "parallelism": f"row bands interleaved over {world} GPU(s), one NCCL framebuffer gather per frame (on a side stream, overlapping the next frame)" if world > 1 else "1 GPU",
                    "l2": "flushed (160 MiB device write > 126 MB L2) between steps, inside the timed region",
                    "timing": "CUDA events bracketing the K frames (frame streams joined before the end event), max over ranks", "pipelining": "consecutive frames alternate two streams / work-buffer sets: frame k+1 starts while frame k drains, resolves and is gathered", "wall_ms_per_step": wall_ms / args.steps},
@@ -306,13 +425,12 @@ def run_ours(args):
         "fp32_issue": {"achieved": flops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / fp32_peak,
                        "flop_per_ray": FLOP_PER_SPHERE_TEST * n + FLOP_PER_RAY_FIXED,
                        "note": "reference-algorithm FLOPs (17 per sphere test x ALL spheres + 150 per ray, SURVEY §8d) over nominal FP32 vector peak 148 SM x 128 lanes x 2 x max SM clock; the kernel culls most sphere tests, so executed FLOPs are lower than credited"},
-        "clocks": clocks,
+        "clocks": clocks, "golden": golden["status"], "golden_detail": golden,
         "rays_per_step": total_rays / args.steps, "candidates_per_ray": cand / max(rays, 1),
         "algorithm": "two-level conservative f32 culling (clusters of 4 spheres) + exact f64 confirmation; identical results to the linear scan",
     }
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_leg(args.config, args.cpu_seconds)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = cpu_baseline_subprocess(args.config, args.cpu_seconds)
     print(json.dumps(line), flush=True)
     rdr.release()
 

@@ -185,6 +185,8 @@ int rtb200_probe_sky(const rt_vec3* dir, uint32_t sky_mode, float out_rgb[3]);
 int rtb200_probe_get_ray(const rt_camera* cam, double u, double v, rt_vec3* origin, rt_vec3* dir);
 /* n uniform draws of the per-(pixel,sample) stream: kind 0 = gen::<f64>() in [0,1), 1 = gen_range(-1.0..1.0) */
 int rtb200_probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t kind, uint32_t n, double* out);
+/* u_v_from_sphere_hit_point (sphere.rs:35-43) of n vectors hp = hit point - centre (3 doubles each); out = n {u, v} pairs */
+int rtb200_probe_sphere_uv(const double* hp_xyz, uint32_t n, double* out_uv);
 /* u8 quantisation of raytracer.rs:207-213 for n linear means */
 int rtb200_probe_quantise(const float* mean_linear, uint32_t n, uint8_t* out);
 

@@ -155,10 +155,85 @@ static inline Ray get_ray(const rt_camera& c, double u, double v) {             
 // ------------------------------------------------------------------------------------------------
 struct Hit { double t; P3 point, normal; bool front_face; int sphere; double u, v; };
 
+// f64::atan2 (sphere.rs:38). Rust forwards to the platform libm, so the reference's last bit is platform-defined.
+// To make texel addresses reproducible on every host AND on the GPU, oracle and kernel share one explicit algorithm:
+// the classic table-free atan (argument reduction at 7/16, 11/16, 19/16, 39/16 + an odd minimax polynomial of degree
+// 23, < 1 ulp) and the usual quadrant logic of atan2, evaluated in plain IEEE f64 without contraction. The device
+// copy is rtd::rt_atan2 (csrc/rtb200_device.cuh); tests compare the two bit for bit, and compare this one with the
+// host libm (tests/test_oracle_semantics.py: <= 1 ulp apart; identical texels on the C1 frame). g_atan2_mode = 0
+// switches the oracle back to the host libm for that comparison.
+static int g_atan2_mode = 1;
+static inline uint32_t hi_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (uint32_t)(b >> 32); }
+static inline uint32_t lo_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (uint32_t)b; }
+static inline double rt_atan(double x) {
+    static const double hi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    static const double lo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    static const double T[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,
+                                 9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,
+                                 4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    const uint32_t hx = hi_word(x), ix = hx & 0x7fffffffu;
+    const bool negative = (hx >> 31) != 0;
+    if (ix >= 0x44100000u) {                       // |x| >= 2^66, inf or NaN
+        if (x != x) return x + x;
+        const double r = hi[3] + lo[3];
+        return negative ? -r : r;
+    }
+    int id;
+    if (ix < 0x3fdc0000u) {                        // |x| < 7/16
+        if (ix < 0x3e400000u) return x;            // |x| < 2^-27
+        id = -1;
+    } else {
+        x = std::fabs(x);
+        if (ix < 0x3ff30000u) {                    // |x| < 19/16
+            if (ix < 0x3fe60000u) { id = 0; x = (2.0 * x - 1.0) / (2.0 + x); }
+            else { id = 1; x = (x - 1.0) / (x + 1.0); }
+        } else if (ix < 0x40038000u) { id = 2; x = (x - 1.5) / (1.0 + 1.5 * x); }   // |x| < 39/16
+        else { id = 3; x = -1.0 / x; }
+    }
+    const double z = x * x, w = z * z;
+    const double s1 = z * (T[0] + w * (T[2] + w * (T[4] + w * (T[6] + w * (T[8] + w * T[10])))));
+    const double s2 = w * (T[1] + w * (T[3] + w * (T[5] + w * (T[7] + w * T[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    const double r = hi[id] - ((x * (s1 + s2) - lo[id]) - x);
+    return negative ? -r : r;
+}
+static inline double rt_atan2(double y, double x) {
+    const double PI_HI = 3.1415926535897931160e+00, PI_LO = 1.2246467991473531772e-16, TINY = 1.0e-300;
+    if (x != x || y != y) return x + y;
+    const uint32_t hx = hi_word(x), hy = hi_word(y), ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (x == 1.0) return rt_atan(y);
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);   // 2*sign(x) + sign(y)
+    if ((iy | lo_word(y)) == 0u) {                 // y = +-0
+        switch (m) { case 0: case 1: return y; case 2: return PI_HI + TINY; default: return -PI_HI - TINY; }
+    }
+    if ((ix | lo_word(x)) == 0u) return (hy >> 31) ? -PI_HI / 2.0 - TINY : PI_HI / 2.0 + TINY;
+    if (ix == 0x7ff00000u) {                       // x = +-inf
+        if (iy == 0x7ff00000u) {
+            switch (m) { case 0: return PI_HI / 4.0 + TINY; case 1: return -PI_HI / 4.0 - TINY;
+                         case 2: return 3.0 * (PI_HI / 4.0) + TINY; default: return -3.0 * (PI_HI / 4.0) - TINY; }
+        }
+        switch (m) { case 0: return 0.0; case 1: return -0.0; case 2: return PI_HI + TINY; default: return -PI_HI - TINY; }
+    }
+    if (iy == 0x7ff00000u) return (hy >> 31) ? -PI_HI / 2.0 - TINY : PI_HI / 2.0 + TINY;
+    const int k = ((int)iy - (int)ix) >> 20;       // exponent difference
+    double z;
+    int mm = m;
+    if (k > 60) { z = PI_HI / 2.0 + 0.5 * PI_LO; mm &= 1; }
+    else if ((hx >> 31) && k < -60) z = 0.0;
+    else z = rt_atan(std::fabs(y / x));
+    switch (mm) {
+        case 0: return z;
+        case 1: return -z;
+        case 2: return PI_HI - (z - PI_LO);
+        default: return (z - PI_LO) - PI_HI;
+    }
+}
+
 static inline void u_v_from_sphere_hit_point(P3 hp, double* u, double* v) {                      // sphere.rs:35-43
     const double PI = 3.14159265358979323846264338327950288;
     P3 n = unit_vector(hp);
-    *u = (std::atan2(n.x, n.z) / (2.0 * PI)) + 0.5;
+    const double at = g_atan2_mode ? rt_atan2(n.x, n.z) : std::atan2(n.x, n.z);
+    *u = (at / (2.0 * PI)) + 0.5;
     *v = n.y * 0.5 + 0.5;
 }
 static inline bool sphere_hit(const rt_sphere& s, int index, const Ray& ray, double t_min, double t_max, Hit* h) {

@@ -124,6 +124,18 @@ int oracle_sphere_hit(const rt_vec3* center, double radius, const rt_vec3* origi
     return 0;
 }
 
+// atan2 as the oracle evaluates it (mode 1, default: the restated algorithm shared with the kernel; mode 0: host libm).
+int oracle_set_atan2_mode(int mode) { int old = g_atan2_mode; g_atan2_mode = mode ? 1 : 0; return old; }
+int oracle_atan2(const double* y, const double* x, uint32_t n, int mode, double* out) {
+    for (uint32_t i = 0; i < n; ++i) out[i] = mode ? rt_atan2(y[i], x[i]) : std::atan2(y[i], x[i]);
+    return 0;
+}
+// u_v_from_sphere_hit_point (sphere.rs:35-43) for n points hp = hit point - centre; out = {u, v} pairs.
+int oracle_sphere_uv(const double* hp_xyz, uint32_t n, double* out_uv) {
+    for (uint32_t i = 0; i < n; ++i) u_v_from_sphere_hit_point(P3{hp_xyz[3 * i], hp_xyz[3 * i + 1], hp_xyz[3 * i + 2]}, &out_uv[2 * i], &out_uv[2 * i + 1]);
+    return 0;
+}
+
 int oracle_refract(const rt_vec3* uv, const rt_vec3* n, double eta, rt_vec3* out) {
     P3 r = refract(p3(*uv), p3(*n), eta);
     *out = rt_vec3{r.x, r.y, r.z};

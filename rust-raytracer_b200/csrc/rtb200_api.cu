@@ -811,6 +811,13 @@ int rtb200_probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t ki
     CU(probe_rng(seed, pixel, sample, kind, n, (double*)dout, c->stream));
     return probe_finish(c, o, dout, (size_t)n * 8);
 }
+int rtb200_probe_sphere_uv(const double* hp_xyz, uint32_t n, double* out_uv) {
+    DeviceCtx* c; void *din, *dout;
+    int rc = probe_io(hp_xyz, (size_t)n * 24, (size_t)n * 16, &c, &din, &dout);
+    if (rc != RT_OK) return rc;
+    CU(probe_sphere_uv((const double*)din, n, (double*)dout, c->stream));
+    return probe_finish(c, out_uv, dout, (size_t)n * 16);
+}
 int rtb200_probe_quantise(const float* mean_linear, uint32_t n, uint8_t* o) {
     DeviceCtx* c; void *din, *dout;
     int rc = probe_io(mean_linear, (size_t)n * 4, n, &c, &din, &dout);

@@ -175,11 +175,90 @@ RT_DEV HitRec hit_record(D3 center, double radius, D3 o, D3 d, double t) {
     h.normal = h.front_face ? n : neg(n);
     return h;
 }
+// f64::atan2 (sphere.rs:38). Rust forwards to the platform libm, so the last bit of the reference is platform-defined;
+// CUDA's atan2 is a third implementation. Texel addresses must not depend on that, so the kernel evaluates one explicit
+// algorithm in plain IEEE f64 (every operation rounded to nearest, never contracted): the table-free atan with argument
+// reduction at 7/16, 11/16, 19/16, 39/16 and an odd polynomial of degree 23 (< 1 ulp), plus the usual quadrant logic.
+// The CPU oracle evaluates the same operations in the same order; tests compare the two bit for bit.
+RT_DEV double rt_atan(double x) {
+    const uint32_t hx = (uint32_t)__double2hiint(x), ix = hx & 0x7fffffffu;
+    const bool negative = (hx >> 31) != 0u;
+    if (ix >= 0x44100000u) {                       // |x| >= 2^66, inf or NaN
+        if (x != x) return __dadd_rn(x, x);
+        const double r = __dadd_rn(1.57079632679489655800e+00, 6.12323399573676603587e-17);
+        return negative ? -r : r;
+    }
+    int id;
+    double h = 0.0, l = 0.0;
+    if (ix < 0x3fdc0000u) {                        // |x| < 7/16
+        if (ix < 0x3e400000u) return x;            // |x| < 2^-27
+        id = -1;
+    } else {
+        x = fabs(x);
+        if (ix < 0x3ff30000u) {                    // |x| < 19/16
+            if (ix < 0x3fe60000u) { id = 0; h = 4.63647609000806093515e-01; l = 2.26987774529616870924e-17; x = __ddiv_rn(__dsub_rn(__dmul_rn(2.0, x), 1.0), __dadd_rn(2.0, x)); }
+            else { id = 1; h = 7.85398163397448278999e-01; l = 3.06161699786838301793e-17; x = __ddiv_rn(__dsub_rn(x, 1.0), __dadd_rn(x, 1.0)); }
+        } else if (ix < 0x40038000u) { id = 2; h = 9.82793723247329054082e-01; l = 1.39033110312309984516e-17; x = __ddiv_rn(__dsub_rn(x, 1.5), __dadd_rn(1.0, __dmul_rn(1.5, x))); }   // |x| < 39/16
+        else { id = 3; h = 1.57079632679489655800e+00; l = 6.12323399573676603587e-17; x = __ddiv_rn(-1.0, x); }
+    }
+    const double z = __dmul_rn(x, x), w = __dmul_rn(z, z);
+    double s1 = __dmul_rn(w, 1.62858201153657823623e-02);
+    s1 = __dmul_rn(w, __dadd_rn(4.97687799461593236017e-02, s1));
+    s1 = __dmul_rn(w, __dadd_rn(6.66107313738753120669e-02, s1));
+    s1 = __dmul_rn(w, __dadd_rn(9.09088713343650656196e-02, s1));
+    s1 = __dmul_rn(w, __dadd_rn(1.42857142725034663711e-01, s1));
+    s1 = __dmul_rn(z, __dadd_rn(3.33333333333329318027e-01, s1));
+    double s2 = __dmul_rn(w, -3.65315727442169155270e-02);
+    s2 = __dmul_rn(w, __dadd_rn(-5.83357013379057348645e-02, s2));
+    s2 = __dmul_rn(w, __dadd_rn(-7.69187620504482999495e-02, s2));
+    s2 = __dmul_rn(w, __dadd_rn(-1.11111104054623557880e-01, s2));
+    s2 = __dmul_rn(w, __dadd_rn(-1.99999999998764832476e-01, s2));
+    const double xs = __dmul_rn(x, __dadd_rn(s1, s2));
+    if (id < 0) return __dsub_rn(x, xs);
+    const double r = __dsub_rn(h, __dsub_rn(__dsub_rn(xs, l), x));
+    return negative ? -r : r;
+}
+RT_DEV double rt_atan2(double y, double x) {
+    const double PI_HI = 3.1415926535897931160e+00, PI_LO = 1.2246467991473531772e-16, TINY = 1.0e-300;
+    if (x != x || y != y) return __dadd_rn(x, y);
+    const uint32_t hx = (uint32_t)__double2hiint(x), hy = (uint32_t)__double2hiint(y), ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (x == 1.0) return rt_atan(y);
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);   // 2*sign(x) + sign(y)
+    if ((iy | (uint32_t)__double2loint(y)) == 0u) {                 // y = +-0
+        if (m < 2) return y;
+        return m == 2 ? __dadd_rn(PI_HI, TINY) : __dsub_rn(-PI_HI, TINY);
+    }
+    const double half_pi = __ddiv_rn(PI_HI, 2.0);
+    if ((ix | (uint32_t)__double2loint(x)) == 0u) return (hy >> 31) ? __dsub_rn(-half_pi, TINY) : __dadd_rn(half_pi, TINY);
+    if (ix == 0x7ff00000u) {                       // x = +-inf
+        const double q = __ddiv_rn(PI_HI, 4.0);
+        if (iy == 0x7ff00000u) {
+            if (m == 0) return __dadd_rn(q, TINY);
+            if (m == 1) return __dsub_rn(-q, TINY);
+            if (m == 2) return __dadd_rn(__dmul_rn(3.0, q), TINY);
+            return __dsub_rn(__dmul_rn(-3.0, q), TINY);
+        }
+        if (m == 0) return 0.0;
+        if (m == 1) return -0.0;
+        return m == 2 ? __dadd_rn(PI_HI, TINY) : __dsub_rn(-PI_HI, TINY);
+    }
+    if (iy == 0x7ff00000u) return (hy >> 31) ? __dsub_rn(-half_pi, TINY) : __dadd_rn(half_pi, TINY);
+    const int k = ((int)iy - (int)ix) >> 20;       // exponent difference
+    double z;
+    int mm = m;
+    if (k > 60) { z = __dadd_rn(half_pi, __dmul_rn(0.5, PI_LO)); mm &= 1; }
+    else if ((hx >> 31) && k < -60) z = 0.0;
+    else z = rt_atan(fabs(__ddiv_rn(y, x)));
+    if (mm == 0) return z;
+    if (mm == 1) return -z;
+    if (mm == 2) return __dsub_rn(PI_HI, __dsub_rn(z, PI_LO));
+    return __dsub_rn(__dsub_rn(z, PI_LO), PI_HI);
+}
 // sphere.rs:35-43 (evaluated lazily: only Texture materials read u,v)
 RT_DEV void sphere_uv(D3 hp, double& u, double& v) {
     const double PI = 3.14159265358979323846264338327950288;
     D3 n = unit_vector(hp);
-    u = __dadd_rn(__ddiv_rn(atan2(n.x, n.z), __dmul_rn(2.0, PI)), 0.5);
+    u = __dadd_rn(__ddiv_rn(rt_atan2(n.x, n.z), __dmul_rn(2.0, PI)), 0.5);
     v = __dadd_rn(__dmul_rn(n.y, 0.5), 0.5);
 }
 

@@ -388,6 +388,15 @@ __global__ void k_probe_quantise(const float* in, uint32_t n, uint8_t* out) {
     if (i < n) out[i] = quantise_u8(in[i]);
 }
 
+__global__ void k_probe_sphere_uv(const double* in, uint32_t n, double* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sphere_uv(mk(in[3 * i], in[3 * i + 1], in[3 * i + 2]), out[2 * i], out[2 * i + 1]);
+}
+cudaError_t probe_sphere_uv(const double* in, uint32_t n, double* out, cudaStream_t st) {
+    k_probe_sphere_uv<<<(n + 255) / 256, 256, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t probe_sphere_hit(const double* in, double* out, cudaStream_t st) { k_probe_sphere_hit<<<1, 1, 0, st>>>(in, out); return cudaGetLastError(); }
 cudaError_t probe_refract(const double* in, double* out, cudaStream_t st) { k_probe_refract<<<1, 1, 0, st>>>(in, out); return cudaGetLastError(); }
 cudaError_t probe_reflectance(const double* in, double* out, cudaStream_t st) { k_probe_reflectance<<<1, 1, 0, st>>>(in, out); return cudaGetLastError(); }

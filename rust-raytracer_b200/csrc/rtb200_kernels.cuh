@@ -102,5 +102,6 @@ cudaError_t probe_sky(const double* in /*3*/, uint32_t mode, float* out /*3*/, c
 cudaError_t probe_get_ray(const rt_camera* cam_dev, const double* in /*2*/, double* out /*6*/, cudaStream_t st);
 cudaError_t probe_rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t kind, uint32_t n, double* out, cudaStream_t st);
 cudaError_t probe_quantise(const float* in, uint32_t n, uint8_t* out, cudaStream_t st);
+cudaError_t probe_sphere_uv(const double* in /*3n*/, uint32_t n, double* out /*2n*/, cudaStream_t st);
 
 }  // namespace rtk

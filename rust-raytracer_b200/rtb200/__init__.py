@@ -93,7 +93,7 @@ ABI_SYMBOLS = [
     "rtb200_scene_release", "rtb200_probe_sphere_hit", "rtb200_probe_refract", "rtb200_probe_reflectance",
     "rtb200_probe_sky", "rtb200_probe_get_ray", "rtb200_probe_rng", "rtb200_probe_quantise",
     "rtb200_decode_jpeg_file", "rtb200_free", "rtb200_render_device_async", "rtb200_render_device_wait",
-    "rtb200_debug_filter_records",
+    "rtb200_debug_filter_records", "rtb200_probe_sphere_uv",
 ]
 
 _lib = None
@@ -148,10 +148,24 @@ def vec3(v) -> rt_vec3:
     return rt_vec3(float(v[0]), float(v[1]), float(v[2]))
 
 
+_camera_backend = None   # bench.py's CPU reference arm installs the oracle's Camera::new here so that it never maps librtb200.so
+
+
+def set_camera_backend(fn):
+    """fn(rt_camera_params*, rt_camera*) -> int replacing rtb200_camera_from_params (None restores the library)."""
+    global _camera_backend
+    _camera_backend = fn
+
+
 def camera_from_params(look_from, look_at, vup, vfov: float, aspect: float) -> rt_camera:
     """Camera::new (reference camera.rs:45-77), evaluated by the library's host code."""
     p = rt_camera_params(vec3(look_from), vec3(look_at), vec3(vup), float(vfov), float(aspect))
     out = rt_camera()
+    if _camera_backend is not None:
+        rc = _camera_backend(C.byref(p), C.byref(out))
+        if rc != 0:
+            raise RtError(rc, "camera backend failed")
+        return out
     _check(lib().rtb200_camera_from_params(C.byref(p), C.byref(out)))
     return out
 

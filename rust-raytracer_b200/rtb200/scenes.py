@@ -77,6 +77,15 @@ def config(name: str) -> dict:
         return _variant(rtiow_config(50), 1920, 1080, 1024, 50)
     if name == "C5":
         return _variant(cover_config(), 3840, 2160, 4096, 50)
+    # reduced sizes of the big configs: golden-frame parity cases (tests/golden/frames.json) and profiling targets
+    if name == "C3S":
+        return _variant(cover_config(), 1920, 1080, 4, 50)
+    if name == "C4S":
+        return _variant(rtiow_config(50), 480, 270, 4, 50)
+    if name == "C4M":
+        return _variant(rtiow_config(50), 960, 540, 16, 50)
+    if name == "C5S":
+        return _variant(cover_config(), 3840, 2160, 1, 50)
     raise KeyError(name)
 
 

@@ -52,3 +52,15 @@ def test_depth_limit_and_black_sky():
     cfg = scenes._variant(scenes.cover_config(), 32, 24, 2, 5); cfg["sky"] = None
     lin, img, _ = O.render(R.Scene.from_config(cfg))
     assert not lin.any() and not img.any()         # no sky, no lights -> black frame (raytracer.rs:138-140)
+
+
+@pytest.mark.parametrize("name", ["C1", "C4S"])
+def test_oracle_reproduces_the_committed_frame_hashes(name):
+    """tests/golden/frames.json (the hashes the GPU tests and bench.py assert) is what the oracle renders today."""
+    import hashlib
+    import json
+    with open(os.path.join(GOLD, "frames.json")) as f:
+        g = json.load(f)[name]
+    lin, img, st = O.render(scenes.scene(name))
+    assert st["rays"] == g["rays"]
+    assert hashlib.sha256(img.tobytes()).hexdigest() == g["sha256_rgb8"] and hashlib.sha256(lin.tobytes()).hexdigest() == g["sha256_linear_f32"]

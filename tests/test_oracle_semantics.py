@@ -95,3 +95,36 @@ def test_draw_order_is_scatter_then_light_test():
                                         look_from=(0, 1, 2), look_at=(0, 0, -3), vfov=50.0))
     _, _, sa = O.render(a); _, _, sb = O.render(b)
     assert sb["draws"] > sa["draws"] and sb["rays"] >= sa["rays"]
+
+
+def test_restated_atan2_tracks_the_host_libm_and_does_not_move_a_texel():
+    """f64::atan2 (sphere.rs:38) is libm-defined in the reference; oracle and kernel share one explicit algorithm instead
+    (rto::rt_atan2). It stays within 2 ulp of this host's libm, agrees on every special value, and the C1 frame (the only
+    BASELINE config with textures) is identical whichever of the two the oracle uses."""
+    import ctypes as C
+    from rtb200 import scenes
+    L = O.lib()
+    rng = np.random.default_rng(1)
+    n = 200_000
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    y = np.ascontiguousarray(v[:, 0]); x = np.ascontiguousarray(v[:, 2])
+    a = np.zeros(n); b = np.zeros(n)
+    P = C.POINTER(C.c_double)
+    L.oracle_atan2(y.ctypes.data_as(P), x.ctypes.data_as(P), n, 1, a.ctypes.data_as(P))
+    L.oracle_atan2(y.ctypes.data_as(P), x.ctypes.data_as(P), n, 0, b.ctypes.data_as(P))
+    assert np.abs(a.view(np.int64) - b.view(np.int64)).max() <= 2
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-310, -1e-310, 1e300, -1e300, 0.5, 2.0, -3.0, 1e-30])
+    yy, xx = [np.ascontiguousarray(t.ravel()) for t in np.meshgrid(sp, sp)]
+    a = np.zeros(len(yy)); b = np.zeros(len(yy))
+    L.oracle_atan2(yy.ctypes.data_as(P), xx.ctypes.data_as(P), len(yy), 1, a.ctypes.data_as(P))
+    L.oracle_atan2(yy.ctypes.data_as(P), xx.ctypes.data_as(P), len(yy), 0, b.ctypes.data_as(P))
+    same = (a == b) | (np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= 1e-15 * np.abs(b))
+    assert same.all() and np.array_equal(np.signbit(a[~np.isnan(a)]), np.signbit(b[~np.isnan(b)]))
+    sc = scenes.scene("C1")
+    try:
+        L.oracle_set_atan2_mode(0)
+        lin0, img0, st0 = O.render(sc)
+    finally:
+        L.oracle_set_atan2_mode(1)
+    lin1, img1, st1 = O.render(sc)
+    assert np.array_equal(lin0, lin1) and np.array_equal(img0, img1) and st0["rays"] == st1["rays"]
