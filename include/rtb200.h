@@ -14,7 +14,10 @@
  *     except opaque handles released with the matching *_release call;
  *   - every function returns 0 on success, a negative rt_status otherwise, and
  *     rtb200_last_error() then returns a thread-local message (the reference panics instead);
- *   - calls are blocking; one caller thread at a time per process;
+ *   - calls are blocking unless stated otherwise. Thread safety: every device has its own execution context guarded
+ *     by a mutex, so two host threads may render on two DIFFERENT devices concurrently; calls that use the same
+ *     device are serialised. A scene handle must not be used from two threads at once. The caller's current CUDA
+ *     device is restored before every entry point returns;
  *   - there is NO CPU fallback: without a CUDA device / the sm_100a kernels every render call fails.
  */
 #ifndef RTB200_H
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 1
+#define RTB200_ABI_VERSION 2   /* 2: rt_image.bytes, rt_stats.nodes/gpus_used, multi-GPU entry point, BVH diagnostics, RT_VARIANT_LANES retired */
 
 /* ---- scene records (reference types flattened) --------------------------------------------- */
 
@@ -64,7 +67,11 @@ typedef struct {
 
 /* Decoded RGB8 image, row-major, 3 B/texel. For Texture materials width/height are the values
  * written in the JSON, NOT the decoded file's (materials.rs:208-209 with loader result .0 only, :32). */
-typedef struct { const uint8_t* rgb8; uint64_t width, height; } rt_image;
+typedef struct {
+    const uint8_t* rgb8;
+    uint64_t width, height;
+    uint64_t bytes;       /* size of the buffer rgb8 points to; the callee reads width*height*3 bytes and rejects bytes < that */
+} rt_image;
 
 /* Sky — raytracer/src/config.rs:22-28 and the miss branch raytracer.rs:134-163 */
 enum rt_sky_mode { RT_SKY_NONE = 0 /* black */, RT_SKY_GRADIENT = 1, RT_SKY_TEXTURE = 2 };
@@ -85,10 +92,10 @@ typedef struct {
 
 enum rt_trace_variant {
     RT_VARIANT_AUTO      = 0,
-    RT_VARIANT_FILTERED  = 1, /* CTA-wavefront kernel: two-level f32 conservative filter + exact f64 confirmation (default) */
-    RT_VARIANT_EXACT_F64 = 2, /* every sphere tested in f64 (validation of the filter)        */
-    RT_VARIANT_LANES     = 3, /* lane-autonomous persistent kernel (no CTA-level sorting); kept for comparison */
-    RT_VARIANT_BRUTE_FORCE = 4 /* CTA-wavefront kernel scanning every sphere (no cluster culling), like the reference's hit_world */
+    RT_VARIANT_FILTERED  = 1, /* CTA-wavefront kernel: warp-cooperative traversal of an 8-wide BVH with conservative f32 tests + exact f64 confirmation (default) */
+    RT_VARIANT_EXACT_F64 = 2, /* every sphere tested in f64 (validation of the conservative tests) */
+    RT_VARIANT_RETIRED_LANES = 3, /* ABI 1's lane-autonomous kernel; retired: RT_ERR_UNSUPPORTED */
+    RT_VARIANT_BRUTE_FORCE = 4 /* CTA-wavefront kernel scanning every sphere in list order (no hierarchy), like the reference's hit_world */
 };
 
 /* Which rows this call renders. Row-band b (band_rows consecutive rows) belongs to shard
@@ -113,9 +120,21 @@ typedef struct {
     uint32_t kernel_launches;
     uint32_t batches;
     uint64_t h2d_bytes, d2h_bytes;
-    uint64_t clusters;      /* second-level blocks visited (two-level culling; diagnostic) */
+    uint64_t clusters;      /* BVH leaves visited (diagnostic) */
     uint64_t frames;        /* frames covered by device_ms / trace_ms / kernel_launches (1 for the blocking calls) */
+    uint64_t nodes;         /* BVH nodes visited (diagnostic) */
+    int32_t  gpus_used;     /* devices that rendered this frame */
+    int32_t  reserved;
 } rt_stats;
+
+/* The trace kernel a scene handle launches (cudaFuncGetAttributes + the launch geometry chosen at upload). */
+typedef struct {
+    int32_t  registers, local_bytes;       /* per thread */
+    uint32_t smem_bytes, grid, block, ctas_per_sm;
+    uint32_t smem_mask;                    /* bit0 hierarchy, bit1 exact geometry, bit2 materials staged into shared memory */
+    uint32_t bvh_nodes, bvh_leaves, bvh_depth;
+    char     name[96];
+} rt_kernel_info;
 
 enum rt_status {
     RT_OK = 0,
@@ -142,6 +161,14 @@ uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_
  * out_rgb8: width*height*3 bytes (or shard_rows*width*3 when opts->world > 1). */
 int rtb200_render_rgb8(const rt_scene* scene, const rt_options* opts, uint8_t* out_rgb8, rt_stats* stats);
 
+/* The same frame on n_gpus devices of this process (0 = all; devices opts->device.. when opts->device >= 0, else 0..):
+ * the reference's row bands (raytracer.rs:254-262) are dealt round-robin to the devices (band b -> device b mod G), the
+ * scene is replicated, every device renders its shard, the shards are copied peer-to-peer into the frame on the first
+ * device and ONE device->host copy fills out_rgb8 (width*height*3 bytes). Bit-identical to rtb200_render_rgb8.
+ * opts->rank/world must be 0/1 (or opts NULL). */
+int rtb200_device_count(void);
+int rtb200_render_rgb8_multi(const rt_scene* scene, const rt_options* opts, int32_t n_gpus, uint8_t* out_rgb8, rt_stats* stats);
+
 /* Same path, but returns the per-pixel mean radiance BEFORE sqrt/quantisation (raytracer.rs:207-212
  * computes sqrt(scale*sum)); used by parity tests. out_rgb: width*height*3 floats (or the shard's). */
 int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, float* out_rgb, rt_stats* stats);
@@ -159,19 +186,22 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
 int rtb200_render_device_async(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream);
 int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats);
 int rtb200_scene_release(rtb200_scene_handle h);
+int rtb200_scene_kernel_info(rtb200_scene_handle h, rt_kernel_info* out);
 
 /* load_texture_image — materials.rs:213-219, config.rs:36-47: decode a baseline JPEG file to RGB8 (host-side scene staging
  * helper for hosts without their own decoder; the reference uses the jpeg-decoder crate). *out_rgb8 is released with rtb200_free(). */
 int  rtb200_decode_jpeg_file(const char* path, uint8_t** out_rgb8, uint64_t* width, uint64_t* height);
 void rtb200_free(void* p);
 
-/* Diagnostic, host only (no GPU needed): the conservative filter records the closest-hit stage of hit_world (raytracer.rs:44-59)
- * would use for `scene`: recentring offset, first level (pair-packed {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}: cluster bounds, or the spheres
- * themselves), second level (member spheres, cluster_size slots per cluster), slot -> sphere index, |c| of each bound.
- * info = {two_level, first_level_pairs, n_clusters, cluster_size}. Arrays are filled up to their capacities (elements). */
-int rtb200_debug_filter_records(const rt_scene* scene, uint32_t variant, double recentre[3], uint32_t info[4],
-                                float* first, uint64_t cap_first, float* second, uint64_t cap_second,
-                                uint16_t* slot_to_sphere, uint64_t cap_slots, float* cluster_abs, uint64_t cap_clusters);
+/* Diagnostic, host only (no GPU needed): what the closest-hit stage of hit_world (raytracer.rs:44-59) would read for `scene`:
+ * recentring offset; the 8-wide BVH nodes (floats_per_node floats each: lo_x[8] lo_y[8] lo_z[8] hi_x[8] hi_y[8] hi_z[8]
+ * child[8], child = 0xffffffff empty | 0x80000000+leaf | node); the leaves (leaf_size pair-packed sphere records
+ * {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1} + slot -> sphere index, 0xffffffff = padding); the spheres tested for every ray; the
+ * flat records of RT_VARIANT_BRUTE_FORCE. info = {n_nodes, n_leaves, depth, leaf_size, n_always, floats_per_node, flat_pairs, 0}.
+ * Arrays are filled up to their capacities (elements). */
+int rtb200_debug_bvh(const rt_scene* scene, double recentre[3], uint32_t info[8], float* nodes, uint64_t cap_nodes,
+                     float* leaf_rec, uint64_t cap_leaf_rec, uint32_t* leaf_id, uint64_t cap_leaf_id,
+                     uint32_t* always, uint64_t cap_always, float* flat, uint64_t cap_flat);
 
 /* Device-function probes: run the kernel's own device routines on one thread and return the result,
  * so the reference's known-answer tests can be asserted against the GPU code itself.

@@ -1,5 +1,7 @@
 // Part of the Rust-side binding described in INTEGRATION.md (N3). Not compiled in this repository: the build image has no
-// cargo/rustc. Drop into dps/rust-raytracer's `raytracer/` crate as the file name says.
+// cargo/rustc. Drop into dps/rust-raytracer's `raytracer/` crate as `src/rtb200_sys.rs`.
+// Mirrors include/rtb200.h (ABI 2) one to one; tests/test_rust_shim_layout.py parses THIS file and checks every field
+// offset, size and alignment against the header's structs, and both extern signatures against the header's prototypes.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int};
 
@@ -9,7 +11,7 @@ use std::os::raw::{c_char, c_int};
     pub center: rt_vec3, pub radius: f64,
     pub kind: u32, pub albedo: [f32; 3], pub param: f64, pub texture: i32, pub reserved: i32,
 }
-#[repr(C)] #[derive(Clone, Copy)] pub struct rt_image { pub rgb8: *const u8, pub width: u64, pub height: u64 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct rt_image { pub rgb8: *const u8, pub width: u64, pub height: u64, pub bytes: u64 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct rt_sky { pub mode: u32, pub reserved: u32, pub tex: rt_image }
 #[repr(C)] pub struct rt_scene {
     pub width: u32, pub height: u32, pub samples_per_pixel: u32, pub max_depth: u32,
@@ -22,11 +24,12 @@ use std::os::raw::{c_char, c_int};
     pub rays: u64, pub samples: u64, pub candidates: u64,
     pub device_ms: f64, pub trace_ms: f64, pub wall_ms: f64,
     pub kernel_launches: u32, pub batches: u32, pub h2d_bytes: u64, pub d2h_bytes: u64,
-    pub clusters: u64, pub frames: u64,
+    pub clusters: u64, pub frames: u64, pub nodes: u64, pub gpus_used: i32, pub reserved: i32,
 }
 #[repr(C)] pub struct rt_options { pub device: i32, pub rank: i32, pub world: i32, pub band_rows: u32, pub variant: u32, pub flags: u32, pub sample_buffer_bytes: u64 }
 
 extern "C" {
     pub fn rtb200_render_rgb8(scene: *const rt_scene, opts: *const rt_options, out_rgb8: *mut u8, stats: *mut rt_stats) -> c_int;
+    pub fn rtb200_render_rgb8_multi(scene: *const rt_scene, opts: *const rt_options, n_gpus: i32, out_rgb8: *mut u8, stats: *mut rt_stats) -> c_int;
     pub fn rtb200_last_error() -> *const c_char;
 }

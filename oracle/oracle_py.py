@@ -37,7 +37,10 @@ _lib = None
 
 
 def build(force: bool = False):
-    if force or not os.path.exists(LIB_PATH):
+    """(Re)build liboracle.so when it is missing or older than its sources / include/rtb200.h (the structs it reads)."""
+    deps = [os.path.join(_HERE, f) for f in ("rt_oracle_capi.cpp", "rt_oracle.hpp", "Makefile")] + [os.path.join(_REPO, "include", "rtb200.h")]
+    stale = not os.path.exists(LIB_PATH) or any(os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 

@@ -1,18 +1,22 @@
 // rtb200_api.cu — the C ABI of include/rtb200.h: scene staging into HBM, batch scheduling of the trace /
-// resolve kernels, device<->host copies and error reporting. No CPU render path exists in this library.
+// resolve kernels, single- and multi-GPU frames, device<->host copies and error reporting. No CPU render path exists here.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
+#include "rtb200_bvh.hpp"
 #include "rtb200_kernels.cuh"
 
 using namespace rtk;
+
+static_assert(sizeof(rtbvh::Mat32) == sizeof(DevMat), "host and device material records must agree");
+static_assert(rtbvh::kLeafK == kLeafK && rtbvh::kNodeFloats == kNodeVec * 4, "host and device BVH layouts must agree");
 
 namespace {
 
@@ -44,9 +48,23 @@ struct GrowBuf {
         return cudaSuccess;
     }
 };
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        cap = bytes + bytes / 8;
+        return cudaSuccess;
+    }
+};
 
-// Per-device execution context: one stream, grow-only work buffers, timing events. One render at a time.
+// Per-device execution context: one stream, grow-only work buffers. `mu` serialises the calls that use the context, so two
+// host threads may render on two DIFFERENT devices concurrently; calls on the same device take turns.
 struct DeviceCtx {
+    std::recursive_mutex mu;
     bool init = false;
     int device = -1;
     int sm_count = 0;
@@ -55,11 +73,15 @@ struct DeviceCtx {
     // Two sets of per-frame work buffers: a frame loop that alternates two streams lets frame k+1 start tracing while frame k
     // drains its last paths and resolves (rtb200_render_device_async); blocking calls use set 0 only.
     struct WorkSet { GrowBuf samplebuf, accum, stack, small, frames, lterm; } ws[2];
-    GrowBuf out_rgb8, out_lin, probe;
-    std::vector<cudaEvent_t> ev;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    GrowBuf out_rgb8, out_lin, probe, frame;
+    // scene arenas of released handles, kept for the next upload (a per-frame upload costs no cudaMalloc / cudaFree)
+    struct Arena { void* p; size_t cap; };
+    std::vector<Arena> arena_cache;
+    PinnedBuf staging;                    // host image of the arena being uploaded
+    cudaEvent_t staging_free = nullptr;   // the last H2D copy out of `staging` has finished
 };
 DeviceCtx g_ctx[64];
+std::mutex g_ctx_mu;
 
 int get_ctx(int device, DeviceCtx** out) {
     if (device < 0) {
@@ -72,6 +94,7 @@ int get_ctx(int device, DeviceCtx** out) {
     if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
     if (device >= count) return fail(RT_ERR_NO_DEVICE, "no such CUDA device");
     CU(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
     DeviceCtx& c = g_ctx[device];
     if (!c.init) {
         cudaDeviceProp prop;
@@ -85,13 +108,19 @@ int get_ctx(int device, DeviceCtx** out) {
         c.sm_count = prop.multiProcessorCount;
         c.max_smem = prop.sharedMemPerBlockOptin;
         CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        CU(cudaEventCreate(&c.ev_begin));
-        CU(cudaEventCreate(&c.ev_end));
+        CU(cudaEventCreateWithFlags(&c.staging_free, cudaEventDisableTiming));
         c.init = true;
     }
     *out = &c;
     return RT_OK;
 }
+
+// RAII: restores the caller's current device (the ABI must not leave cudaSetDevice changed behind the caller's back)
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 struct V3 { double x, y, z; };
 inline V3 v3(const rt_vec3& a) { return V3{a.x, a.y, a.z}; }
@@ -103,10 +132,8 @@ inline V3 vunit(V3 a) { double l = vlen(a); return V3{a.x / l, a.y / l, a.z / l}
 inline V3 vcross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 inline rt_vec3 rv(V3 a) { return rt_vec3{a.x, a.y, a.z}; }
 
-float f32_up(double x) {   // smallest float >= x
-    float f = (float)x;
-    if ((double)f < x) f = std::nextafterf(f, INFINITY);
-    return f;
+uint32_t mode_of(uint32_t variant) {
+    return variant == RT_VARIANT_EXACT_F64 ? MODE_EXACT : (variant == RT_VARIANT_BRUTE_FORCE ? MODE_BRUTE : MODE_TREE);
 }
 
 }  // namespace
@@ -116,209 +143,41 @@ struct rtb200_scene_t {
     DeviceCtx* ctx = nullptr;
     TraceParams tp{};
     rt_options opts{};
-    bool exact = false;
-    bool lanes = false;
-    int block = 256;
-    int minb = 4;
+    uint32_t mode = MODE_TREE;
+    int minb = 3;
     int grid = 0;
+    int ctas_per_sm = 0;
     size_t smem = 0;
     uint32_t spp_batch = 0;
-    std::vector<void*> owned;   // device allocations owned by the handle
+    void* arena = nullptr;               // ONE device allocation holding every scene array (returned to the context's cache on release)
+    size_t arena_cap = 0;
+    unsigned long long* err = nullptr;   // device: [0] shadow-frame-stack overflows, [1] traversal guard trips; accumulated over frames, cleared by wait
     struct Upload { const void* src; size_t bytes; void** field; };
     std::vector<Upload> uploads;         // pending scene arrays (commit_uploads)
-    std::vector<uint8_t> staging;        // host image of the device arena
-    cudaStream_t last_stream = nullptr;   // stream, work set, batch and launch count of the most recently enqueued frame
+    std::vector<cudaEvent_t> ev;         // event ring of the frames in flight (per handle)
+    cudaStream_t last_stream = nullptr;  // stream, work set, batch and launch count of the most recently enqueued frame
     int last_set = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};   // distinct streams used by the pending frames
     int n_streams = 0;
     uint32_t frame_counter = 0;
     uint32_t last_batches = 0, last_launches = 0;
-    uint32_t pending_frames = 0;          // frames enqueued since the last wait (their events sit in the context's event ring)
+    uint32_t pending_frames = 0;
     uint64_t h2d_bytes = 0;
 };
-
-// Host-side construction of every array the closest-hit stage reads (no CUDA calls): recentring offset, first-level filter
-// records (cluster bounds, or the spheres themselves), second-level records + slot map + |c| of the bounds, exact geometry
-// and materials. Kept separate from the upload so that CPU tests can check the soundness of the records
-// (rtb200_debug_filter_records, tests/test_filter_records_cpu.py).
-struct FilterRecords {
-    double g[3] = {0, 0, 0};
-    bool two_level = false;
-    uint32_t n_pairs = 0, n_clusters = 0;
-    std::vector<float> first;     // n_pairs * 8 floats, pair-packed {cx0,cx1,cy0,cy1},{cz0,cz1,nk0,nk1}
-    std::vector<float> sfilt;     // n_clusters * kClusterK * 4 floats
-    std::vector<uint16_t> orig;   // n_clusters * kClusterK
-    std::vector<float> cmeta;     // n_clusters
-    std::vector<double> geo;      // n * 4
-    std::vector<DevMat> mat;      // n
-};
-
-static void build_filter_records(const rt_scene* s, bool allow_two_level, FilterRecords& R) {
-    const uint32_t n = (uint32_t)s->n_spheres;
-    double g[3] = {0, 0, 0};
-    // ---- recentring offset of the f32 filter frame: component-wise median of the centres ----
-    if (n) {
-        std::vector<double> tmp(n);
-        for (int c = 0; c < 3; ++c) {
-            for (uint32_t i = 0; i < n; ++i) tmp[i] = c == 0 ? s->spheres[i].center.x : (c == 1 ? s->spheres[i].center.y : s->spheres[i].center.z);
-            std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
-            g[c] = tmp[n / 2];
-            if (!std::isfinite(g[c])) g[c] = 0.0;
-        }
-    }
-
-    // ---- device records ----
-    const double U = 5.9604644775390625e-8;   // 2^-24
-    uint32_t n_pairs = ((n + 1) / 2 + 7) / 8 * 8;   // the scan loop consumes 2 blocks of 4 pairs per trip; padding records never hit
-    if (n_pairs == 0) n_pairs = 8;
-    std::vector<float> filt((size_t)n_pairs * 8);
-    std::vector<double> geo((size_t)std::max<uint32_t>(n, 1) * 4, 0.0);
-    std::vector<DevMat> mat(std::max<uint32_t>(n, 1));
-    memset(mat.data(), 0, mat.size() * sizeof(DevMat));
-    for (uint32_t pp = 0; pp < n_pairs; ++pp) {
-        for (int k = 0; k < 2; ++k) {
-            uint32_t i = 2 * pp + k;
-            float cx = 0.f, cy = 0.f, cz = 0.f, nk = -INFINITY;
-            if (i < n) {
-                const rt_sphere& sp = s->spheres[i];
-                double x = sp.center.x - g[0], y = sp.center.y - g[1], z = sp.center.z - g[2];
-                double c2 = x * x + y * y + z * z, r2 = sp.radius * sp.radius;
-                // candidate iff  b^2 + 2c.o - K - |o|^2 >= -(Es + Er):  nk = -K + Es rounded up
-                double Es = 96.0 * U * c2 + 16.0 * U * r2 + 1e-30;
-                double nkd = -(c2 - r2) + Es;
-                cx = (float)x; cy = (float)y; cz = (float)z;
-                nk = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
-                if (!(std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz)) || !(c2 < 1e30)) { cx = cy = cz = 0.f; nk = INFINITY; }   // always a candidate
-                geo[4 * (size_t)i + 0] = sp.center.x; geo[4 * (size_t)i + 1] = sp.center.y; geo[4 * (size_t)i + 2] = sp.center.z;
-                geo[4 * (size_t)i + 3] = sp.radius;
-                DevMat& m = mat[i];
-                m.kind = sp.kind; m.param = sp.param; m.tex = sp.texture; m.pad = 0;
-                if (sp.kind == RT_LAMBERTIAN || sp.kind == RT_METAL) { m.r = sp.albedo[0]; m.g = sp.albedo[1]; m.b = sp.albedo[2]; }
-                else { m.r = m.g = m.b = 1.0f; }   // Glass/Light attenuation is (1,1,1) (materials.rs:67,179); Texture uses texels
-            }
-            // layout: A = {cx0,cx1,cy0,cy1}, B = {cz0,cz1,nk0,nk1}
-            float* A = &filt[(size_t)pp * 8];
-            A[0 + k] = cx; A[2 + k] = cy; A[4 + k] = cz; A[6 + k] = nk;
-        }
-    }
-
-    // ---- two-level culling (N4): spheres grouped into clusters of 8 with bounding spheres ----------------------------
-    // The cluster bound is tested with the SAME conservative 7-FMA filter as a sphere (a bounding sphere is a sphere),
-    // so culling stays a superset of what the exact f64 test can accept; results are identical by construction.
-    // Spheres are grouped by radius octave, then by Morton order of their centres; classes with <= 2 members and
-    // non-finite spheres become singleton clusters. Cluster k owns sphere-record slots [8k, 8k+8) (padded with
-    // never-hit records); orig[] maps a slot back to the sphere index (ties still go to the lowest ORIGINAL index).
-    auto make_record = [&](double x, double y, double z, double r2, float rec[4]) {
-        double c2 = x * x + y * y + z * z;
-        double Es = 96.0 * U * c2 + 16.0 * U * r2 + 1e-30;
-        double nkd = -(c2 - r2) + Es;
-        rec[0] = (float)x; rec[1] = (float)y; rec[2] = (float)z;
-        rec[3] = std::isfinite(nkd) ? f32_up(nkd) : INFINITY;
-        if (!(std::isfinite(rec[0]) && std::isfinite(rec[1]) && std::isfinite(rec[2])) || !(c2 < 1e30)) { rec[0] = rec[1] = rec[2] = 0.f; rec[3] = INFINITY; }
-    };
-    bool two_level = n > 32 && allow_two_level;
-    if (const char* e2 = getenv("RTB200_TWO_LEVEL")) two_level = two_level && atoi(e2) != 0;
-    std::vector<float> cfilt, sfilt;
-    std::vector<uint16_t> orig;
-    std::vector<float> cmeta;
-    uint32_t n_clusters = 0, n_cpairs = 0;
-    if (two_level) {
-        constexpr int K = kClusterK;
-        std::vector<std::vector<uint32_t>> clusters;
-        std::map<int, std::vector<uint32_t>> classes;
-        for (uint32_t i = 0; i < n; ++i) {
-            const rt_sphere& sp = s->spheres[i];
-            bool fin = std::isfinite(sp.center.x) && std::isfinite(sp.center.y) && std::isfinite(sp.center.z) && std::isfinite(sp.radius);
-            if (!fin || sp.radius == 0.0) { clusters.push_back({i}); continue; }
-            classes[std::ilogb(std::fabs(sp.radius))].push_back(i);
-        }
-        for (auto& kv : classes) {
-            std::vector<uint32_t>& mem = kv.second;
-            if (mem.size() <= 2) { for (uint32_t i : mem) clusters.push_back({i}); continue; }
-            // top-down median split on the widest axis until a leaf holds <= K spheres: compact leaves of K/2..K members
-            std::vector<std::pair<size_t, size_t>> work{{0, mem.size()}};
-            auto coord = [&](uint32_t i, int a) { return a == 0 ? s->spheres[i].center.x : a == 1 ? s->spheres[i].center.y : s->spheres[i].center.z; };
-            while (!work.empty()) {
-                auto [b0, e0] = work.back(); work.pop_back();
-                if (e0 - b0 <= (size_t)K) { clusters.emplace_back(mem.begin() + b0, mem.begin() + e0); continue; }
-                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-                for (size_t t = b0; t < e0; ++t) for (int a = 0; a < 3; ++a) { double v = coord(mem[t], a); lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
-                int ax = 0;
-                for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
-                // split so that both halves are multiples of K where possible (fewer padded slots)
-                size_t cnt = e0 - b0, half = ((cnt / 2 + K - 1) / K) * K;
-                if (half >= cnt) half = cnt / 2;
-                std::nth_element(mem.begin() + b0, mem.begin() + b0 + half, mem.begin() + e0, [&](uint32_t x, uint32_t y) { double cx = coord(x, ax), cy = coord(y, ax); return cx < cy || (cx == cy && x < y); });
-                work.emplace_back(b0, b0 + half); work.emplace_back(b0 + half, e0);
-            }
-        }
-        while (clusters.size() % 4 != 0) clusters.push_back({});   // keep every per-cluster array a multiple of 16 bytes (TMA bulk copies)
-        n_clusters = (uint32_t)clusters.size();
-        n_cpairs = ((n_clusters + 1) / 2 + 7) / 8 * 8;
-        cfilt.assign((size_t)n_cpairs * 8, 0.f);
-        sfilt.assign((size_t)n_clusters * K * 4, 0.f);    // K records = K/2 pairs = K float4 per cluster
-        orig.assign((size_t)n_clusters * K, 0xffff);
-        cmeta.assign(n_clusters, 0.f);
-        for (uint32_t pp = 0; pp < n_cpairs; ++pp) { float* A = &cfilt[(size_t)pp * 8]; A[6] = A[7] = -INFINITY; }
-        for (uint32_t k = 0; k < n_clusters; ++k) {
-            const std::vector<uint32_t>& cl = clusters[k];
-            if (cl.empty()) {   // padding cluster: never hit
-                float* A = &cfilt[(size_t)(k / 2) * 8]; int kk = k & 1; A[0 + kk] = A[2 + kk] = A[4 + kk] = 0.f; A[6 + kk] = -INFINITY;
-                for (int j = 0; j < K; ++j) { float* B = &sfilt[(size_t)k * K * 4 + (size_t)(j / 2) * 8]; B[6 + (j & 1)] = -INFINITY; }
-                continue;
-            }
-            // bounding sphere: centroid + max(|ci - c| + |ri|), inflated; non-finite members make the cluster "always hit"
-            double c[3] = {0, 0, 0};
-            bool fin = true;
-            for (uint32_t i : cl) { c[0] += s->spheres[i].center.x; c[1] += s->spheres[i].center.y; c[2] += s->spheres[i].center.z; }
-            for (int a = 0; a < 3; ++a) c[a] /= (double)cl.size();
-            double R = 0;
-            for (uint32_t i : cl) {
-                const rt_sphere& sp = s->spheres[i];
-                double dx = sp.center.x - c[0], dy = sp.center.y - c[1], dz = sp.center.z - c[2];
-                double dist = std::sqrt(dx * dx + dy * dy + dz * dz) + std::fabs(sp.radius);
-                if (!std::isfinite(dist)) fin = false;
-                R = std::max(R, dist);
-            }
-            R = R * (1.0 + 1e-9) + 1e-12;
-            float rec[4];
-            if (fin) make_record(c[0] - g[0], c[1] - g[1], c[2] - g[2], R * R, rec);
-            else { rec[0] = rec[1] = rec[2] = 0.f; rec[3] = INFINITY; }
-            { float* A = &cfilt[(size_t)(k / 2) * 8]; int kk = k & 1; A[0 + kk] = rec[0]; A[2 + kk] = rec[1]; A[4 + kk] = rec[2]; A[6 + kk] = rec[3]; }
-            {
-                double cx = c[0] - g[0], cy = c[1] - g[1], cz = c[2] - g[2];
-                double cn = std::sqrt(cx * cx + cy * cy + cz * cz);
-                cmeta[k] = (fin && std::isfinite(cn) && cn < 1e15) ? f32_up(cn * (1.0 + 1e-6)) : INFINITY;   // INFINITY disables the behind-origin cull
-            }
-            for (int j = 0; j < K; ++j) {
-                float r4[4] = {0.f, 0.f, 0.f, -INFINITY};
-                if (j < (int)cl.size()) {
-                    const rt_sphere& sp = s->spheres[cl[j]];
-                    make_record(sp.center.x - g[0], sp.center.y - g[1], sp.center.z - g[2], sp.radius * sp.radius, r4);
-                    orig[(size_t)k * K + j] = (uint16_t)cl[j];
-                }
-                float* A = &sfilt[(size_t)k * K * 4 + (size_t)(j / 2) * 8]; int kk = j & 1;
-                A[0 + kk] = r4[0]; A[2 + kk] = r4[1]; A[4 + kk] = r4[2]; A[6 + kk] = r4[3];
-            }
-        }
-    }
-
-    R.g[0] = g[0]; R.g[1] = g[1]; R.g[2] = g[2];
-    R.two_level = two_level;
-    R.n_clusters = n_clusters;
-    R.n_pairs = two_level ? n_cpairs : n_pairs;
-    R.first = two_level ? std::move(cfilt) : std::move(filt);
-    R.sfilt = std::move(sfilt); R.orig = std::move(orig); R.cmeta = std::move(cmeta);
-    R.geo = std::move(geo); R.mat = std::move(mat);
-}
 
 extern "C" {
 
 int rtb200_abi_version(void) { return RTB200_ABI_VERSION; }
 const char* rtb200_last_error(void) { return g_last_error.c_str(); }
 
+int rtb200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
 // Camera::new — camera.rs:45-77. Host, once per frame, f64, same operation order as the reference.
-// (Compiled with -fmad=false / no host contraction: see the Makefile.)
+// (Compiled with -ffp-contract=off: see the Makefile.)
 int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out) {
     if (!p || !out) return fail(RT_ERR_INVALID, "null argument");
     const double PI = 3.14159265358979323846264338327950288;
@@ -340,165 +199,190 @@ int rtb200_camera_from_params(const rt_camera_params* p, rt_camera* out) {
 uint32_t rtb200_shard_rows(uint32_t height, int32_t rank, int32_t world, uint32_t band_rows) {
     if (world <= 1) return height;
     if (band_rows == 0) band_rows = 1;
-    uint32_t rows = 0;
-    for (uint32_t y = 0; y < height; ++y)
-        if ((int32_t)((y / band_rows) % (uint32_t)world) == rank) ++rows;
-    return rows;
+    const uint64_t bands = ((uint64_t)height + band_rows - 1) / band_rows;   // last band may be partial
+    if ((uint64_t)rank >= bands) return 0;
+    const uint64_t mine = (bands - 1 - (uint64_t)rank) / (uint64_t)world + 1;   // bands rank, rank+world, ...
+    uint64_t rows = mine * band_rows;
+    const uint64_t last = bands - 1;
+    if (last % (uint64_t)world == (uint64_t)rank) rows -= bands * band_rows - height;   // the partial band is ours
+    return (uint32_t)rows;
 }
 
 static int render_collect(rtb200_scene_handle h, rt_stats* stats);
 
-// Diagnostic (host only, no GPU needed): the filter records rtb200_scene_upload would stage for `scene`.
-// info = {two_level, n_first_level_pairs, n_clusters, cluster_size}; arrays are filled up to their capacities (in elements).
-int rtb200_debug_filter_records(const rt_scene* s, uint32_t variant, double recentre[3], uint32_t info[4],
-                                float* first, uint64_t cap_first, float* second, uint64_t cap_second,
-                                uint16_t* slot_to_sphere, uint64_t cap_slots, float* cluster_abs, uint64_t cap_clusters) {
+// Diagnostic (host only, no GPU needed): the hierarchy rtb200_scene_upload would stage for `scene`.
+// info = {n_nodes, n_leaves, depth, leaf_size, n_always, floats_per_node, n_pairs_flat, 0}; arrays are filled up to their capacities (elements).
+int rtb200_debug_bvh(const rt_scene* s, double recentre[3], uint32_t info[8], float* nodes, uint64_t cap_nodes, float* leaf_rec,
+                     uint64_t cap_leaf_rec, uint32_t* leaf_id, uint64_t cap_leaf_id, uint32_t* always, uint64_t cap_always,
+                     float* flat, uint64_t cap_flat) {
     if (!s || !info) return fail(RT_ERR_INVALID, "null argument");
-    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
-    FilterRecords R;
-    build_filter_records(s, variant != RT_VARIANT_BRUTE_FORCE && variant != RT_VARIANT_LANES && variant != RT_VARIANT_EXACT_F64, R);
+    if (s->n_spheres >= (1ull << 26)) return fail(RT_ERR_UNSUPPORTED, "2^26 or more spheres (list entries carry 27-bit ids)");
+    if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
+    rtbvh::Records R;
+    rtbvh::build_records(s, true, R);
     if (recentre) { recentre[0] = R.g[0]; recentre[1] = R.g[1]; recentre[2] = R.g[2]; }
-    info[0] = R.two_level ? 1u : 0u; info[1] = R.n_pairs; info[2] = R.n_clusters; info[3] = (uint32_t)kClusterK;
-    if (first) memcpy(first, R.first.data(), std::min<uint64_t>(cap_first, R.first.size()) * 4);
-    if (second) memcpy(second, R.sfilt.data(), std::min<uint64_t>(cap_second, R.sfilt.size()) * 4);
-    if (slot_to_sphere) memcpy(slot_to_sphere, R.orig.data(), std::min<uint64_t>(cap_slots, R.orig.size()) * 2);
-    if (cluster_abs) memcpy(cluster_abs, R.cmeta.data(), std::min<uint64_t>(cap_clusters, R.cmeta.size()) * 4);
+    info[0] = R.n_nodes; info[1] = R.n_leaves; info[2] = R.depth; info[3] = (uint32_t)rtbvh::kLeafK; info[4] = (uint32_t)R.always.size();
+    info[5] = (uint32_t)rtbvh::kNodeFloats; info[6] = R.n_pairs; info[7] = 0;
+    if (nodes) memcpy(nodes, R.nodes.data(), std::min<uint64_t>(cap_nodes, R.nodes.size()) * 4);
+    if (leaf_rec) memcpy(leaf_rec, R.leaf_rec.data(), std::min<uint64_t>(cap_leaf_rec, R.leaf_rec.size()) * 4);
+    if (leaf_id) memcpy(leaf_id, R.leaf_id.data(), std::min<uint64_t>(cap_leaf_id, R.leaf_id.size()) * 4);
+    if (always) memcpy(always, R.always.data(), std::min<uint64_t>(cap_always, R.always.size()) * 4);
+    if (flat) memcpy(flat, R.flat.data(), std::min<uint64_t>(cap_flat, R.flat.size()) * 4);
     return RT_OK;
 }
 
 int rtb200_scene_release(rtb200_scene_handle h) {
     if (!h) return RT_OK;
-    if (h->device >= 0) cudaSetDevice(h->device);
-    if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
-    for (void* p : h->owned) cudaFree(p);
+    DeviceRestore restore;
+    if (h->ctx) {
+        std::lock_guard<std::recursive_mutex> lk(h->ctx->mu);
+        cudaSetDevice(h->device);
+        if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
+        else if (h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
+        for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+        if (h->arena) {
+            auto& cache = h->ctx->arena_cache;
+            if (h->arena_cap <= (64u << 20) && cache.size() < 4) cache.push_back(DeviceCtx::Arena{h->arena, h->arena_cap});
+            else cudaFree(h->arena);
+        }
+    }
     delete h;
     return RT_OK;
 }
 
-// Scene arrays are collected first and then placed in ONE device arena filled by ONE host->device copy
-// (a per-frame upload costs one cudaMalloc, one copy, one cudaFree). `field` is patched with the device address.
-static int upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** field) {
+// Scene arrays are collected first and then placed in ONE device arena filled by ONE host->device copy from pinned
+// staging memory; arenas of released scenes are reused. `field` is patched with the device address.
+static void upload_array(rtb200_scene_t* h, const void* src, size_t bytes, void** field) {
     *field = nullptr;
     if (bytes == 0) bytes = 16;
     h->uploads.push_back(rtb200_scene_t::Upload{src, bytes, field});
-    return RT_OK;
 }
 
 static int commit_uploads(rtb200_scene_t* h) {
+    DeviceCtx* ctx = h->ctx;
     size_t total = 0;
     for (auto& u : h->uploads) total += (u.bytes + 255) & ~(size_t)255;
-    void* base = nullptr;
-    CU(cudaMalloc(&base, total ? total : 256));
-    h->owned.push_back(base);
+    if (total == 0) total = 256;
+    // smallest cached arena that is large enough, else a new allocation
+    int pick = -1;
+    for (int i = 0; i < (int)ctx->arena_cache.size(); ++i)
+        if (ctx->arena_cache[i].cap >= total && (pick < 0 || ctx->arena_cache[i].cap < ctx->arena_cache[pick].cap)) pick = i;
+    if (pick >= 0) {
+        h->arena = ctx->arena_cache[pick].p; h->arena_cap = ctx->arena_cache[pick].cap;
+        ctx->arena_cache.erase(ctx->arena_cache.begin() + pick);
+    } else {
+        size_t want = total + total / 4;
+        cudaError_t e = cudaMalloc(&h->arena, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = total; CU(cudaMalloc(&h->arena, want)); }
+        h->arena_cap = want;
+    }
+    char* base = (char*)h->arena;
     size_t off = 0;
-    for (auto& u : h->uploads) { *u.field = (char*)base + off; off += (u.bytes + 255) & ~(size_t)255; }   // addresses first: tables may hold them
-    h->staging.assign(total, 0);
+    for (auto& u : h->uploads) { *u.field = base + off; off += (u.bytes + 255) & ~(size_t)255; }   // addresses first: tables may hold them
+    CU(cudaEventSynchronize(ctx->staging_free));   // the previous upload's copy has left the staging buffer
+    CU(ctx->staging.ensure(total));
     off = 0;
     for (auto& u : h->uploads) {
-        if (u.src) { memcpy(h->staging.data() + off, u.src, u.bytes); h->h2d_bytes += u.bytes; }
+        if (u.src) { memcpy((char*)ctx->staging.p + off, u.src, u.bytes); h->h2d_bytes += u.bytes; }
+        else memset((char*)ctx->staging.p + off, 0, u.bytes);
         off += (u.bytes + 255) & ~(size_t)255;
     }
-    if (total) CU(cudaMemcpyAsync(base, h->staging.data(), total, cudaMemcpyHostToDevice, h->ctx->stream));
+    CU(cudaMemcpyAsync(base, ctx->staging.p, off, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->staging_free, ctx->stream));
     h->uploads.clear();
     return RT_OK;
 }
 
-int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
-    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
-    *out = nullptr;
-    rt_options opts{};
-    opts.device = -1; opts.rank = 0; opts.world = 1; opts.band_rows = 1; opts.variant = RT_VARIANT_AUTO;
-    if (opts_in) opts = *opts_in;
-    if (opts.world <= 0) opts.world = 1;
-    if (opts.band_rows == 0) opts.band_rows = 1;
-    if (opts.rank < 0 || opts.rank >= opts.world) return fail(RT_ERR_INVALID, "rank outside [0, world)");
-    if (opts.flags != 0) return fail(RT_ERR_INVALID, "flags must be 0");
+static int validate_scene(const rt_scene* s, uint32_t* n_lights_out) {
     if (s->width < 2 || s->height < 2) return fail(RT_ERR_INVALID, "width and height must be >= 2 (u,v divide by w-1, h-1: raytracer.rs:199-200)");
     if (s->samples_per_pixel == 0) return fail(RT_ERR_INVALID, "samples_per_pixel must be > 0");
     if ((uint64_t)s->width * s->height >= (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
-    if (s->n_spheres > 65534) return fail(RT_ERR_UNSUPPORTED, "more than 65534 spheres (16-bit candidate indices)");
+    if (s->n_spheres >= (1ull << 26)) return fail(RT_ERR_UNSUPPORTED, "2^26 or more spheres (list entries carry 27-bit ids)");
     if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
-
-    uint32_t n = (uint32_t)s->n_spheres;
+    if (s->n_textures && !s->textures) return fail(RT_ERR_INVALID, "textures is null");
+    auto image_ok = [](const rt_image& im) {
+        if (!im.rgb8 || im.width == 0 || im.height == 0) return false;
+        if (im.width > (1ull << 20) || im.height > (1ull << 20)) return false;
+        return im.width * im.height * 3ull <= im.bytes;   // the callee reads width*height*3 bytes: the buffer must hold them
+    };
     uint32_t n_lights = 0;
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint64_t i = 0; i < s->n_spheres; ++i) {
         const rt_sphere& sp = s->spheres[i];
         if (sp.kind > RT_LIGHT) return fail(RT_ERR_INVALID, "unknown material kind");
         if (sp.kind == RT_LIGHT) ++n_lights;
         if (sp.kind == RT_TEXTURE) {
             if (sp.texture < 0 || (uint64_t)sp.texture >= s->n_textures) return fail(RT_ERR_INVALID, "texture index out of range");
-            const rt_image& im = s->textures[sp.texture];
-            if (!im.rgb8 || im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "empty texture image");
+            if (!image_ok(s->textures[sp.texture])) return fail(RT_ERR_INVALID, "texture image is empty or smaller than width*height*3 bytes (rt_image.bytes)");
         }
     }
     if (n_lights >= 10) return fail(RT_ERR_UNSUPPORTED, "10 or more lights: the reference's light recursion (raytracer.rs:99-114) does not terminate when n_lights * 0.1 >= 1");
-    if (n_lights > 0 && opts.variant == RT_VARIANT_LANES) return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES has no light support");
     if (s->sky.mode > RT_SKY_TEXTURE) return fail(RT_ERR_INVALID, "unknown sky mode");
-    if (s->sky.mode == RT_SKY_TEXTURE && (!s->sky.tex.rgb8 || s->sky.tex.width == 0 || s->sky.tex.height == 0))
-        return fail(RT_ERR_INVALID, "sky texture is empty");
+    if (s->sky.mode == RT_SKY_TEXTURE && !image_ok(s->sky.tex)) return fail(RT_ERR_INVALID, "sky texture is empty or smaller than width*height*3 bytes (rt_image.bytes)");
+    *n_lights_out = n_lights;
+    return RT_OK;
+}
 
+static int normalise_options(const rt_options* opts_in, rt_options* o) {
+    memset(o, 0, sizeof *o);
+    o->device = -1; o->rank = 0; o->world = 1; o->band_rows = 1; o->variant = RT_VARIANT_AUTO;
+    if (opts_in) *o = *opts_in;
+    if (o->world <= 0) o->world = 1;
+    if (o->band_rows == 0) o->band_rows = 1;
+    if (o->rank < 0 || o->rank >= o->world) return fail(RT_ERR_INVALID, "rank outside [0, world)");
+    if (o->flags != 0) return fail(RT_ERR_INVALID, "flags must be 0");
+    if (o->variant == RT_VARIANT_RETIRED_LANES) return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES was retired in ABI 2");
+    if (o->variant > RT_VARIANT_BRUTE_FORCE) return fail(RT_ERR_INVALID, "unknown variant");
+    return RT_OK;
+}
+
+// `R` holds the host-side records (built once; the multi-GPU entry point shares them between its devices).
+static int scene_upload_records(const rt_scene* s, const rt_options& opts, uint32_t n_lights, const rtbvh::Records& R, rtb200_scene_handle* out) {
+    *out = nullptr;
     DeviceCtx* ctx = nullptr;
     int rc = get_ctx(opts.device, &ctx);
     if (rc != RT_OK) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (R.depth > (uint32_t)rtbvh::kMaxDepth) return fail(RT_ERR_UNSUPPORTED, "hierarchy deeper than the traversal stack reserve");
 
     rtb200_scene_t* h = new rtb200_scene_t();
-    h->device = ctx->device; h->ctx = ctx; h->opts = opts;
-    h->exact = (opts.variant == RT_VARIANT_EXACT_F64);
-    h->lanes = (opts.variant == RT_VARIANT_LANES);
-    if (opts.variant > RT_VARIANT_BRUTE_FORCE) return fail(RT_ERR_INVALID, "unknown variant");
     struct Guard { rtb200_scene_t* h; bool ok = false; ~Guard() { if (!ok) rtb200_scene_release(h); } } guard{h};
-
-    FilterRecords R;
-    build_filter_records(s, !h->lanes && !h->exact && opts.variant != RT_VARIANT_BRUTE_FORCE, R);
-    const bool two_level = R.two_level;
-    const uint32_t n_clusters = R.n_clusters;
-    uint32_t n_pairs = R.n_pairs;
-    const double* g = R.g;
-    std::vector<float>& filt = R.first; std::vector<float>& cfilt = R.first;
-    std::vector<float>& sfilt = R.sfilt; std::vector<uint16_t>& orig = R.orig; std::vector<float>& cmeta = R.cmeta;
-    std::vector<double>& geo = R.geo; std::vector<DevMat>& mat = R.mat;
-    const double U = 5.9604644775390625e-8;   // 2^-24
-    (void)n_clusters;
+    h->device = ctx->device; h->ctx = ctx; h->opts = opts;
+    h->mode = mode_of(opts.variant);
+    const uint32_t n = (uint32_t)s->n_spheres;
 
     TraceParams& tp = h->tp;
-    void* d = nullptr;
-    tp.two_level = two_level ? 1u : 0u;
-    tp.n_clusters = n_clusters;
-    if (two_level) {
-        if ((rc = upload_array(h, cfilt.data(), cfilt.size() * 4, (void**)&tp.filt)) != RT_OK) return rc;
-        if ((rc = upload_array(h, sfilt.data(), sfilt.size() * 4, (void**)&tp.sfilt)) != RT_OK) return rc;
-        if ((rc = upload_array(h, orig.data(), orig.size() * 2, (void**)&tp.orig)) != RT_OK) return rc;
-        if ((rc = upload_array(h, cmeta.data(), cmeta.size() * 4, (void**)&tp.cmeta)) != RT_OK) return rc;
-    } else {
-        if ((rc = upload_array(h, filt.data(), filt.size() * 4, (void**)&tp.filt)) != RT_OK) return rc;
-        tp.sfilt = nullptr; tp.orig = nullptr; tp.cmeta = nullptr;
-    }
-    if ((rc = upload_array(h, geo.data(), geo.size() * 8, (void**)&tp.geo)) != RT_OK) return rc;
-    if ((rc = upload_array(h, mat.data(), mat.size() * sizeof(DevMat), (void**)&tp.mat)) != RT_OK) return rc;
+    tp.n = n; tp.n_pairs = R.n_pairs; tp.n_nodes = R.n_nodes; tp.n_leaves = R.n_leaves; tp.n_always = (uint32_t)R.always.size();
+    tp.depth = R.depth; tp.n_lights = n_lights;
+    upload_array(h, R.nodes.data(), R.nodes.size() * 4, (void**)&tp.nodes);
+    upload_array(h, R.leaf_rec.data(), R.leaf_rec.size() * 4, (void**)&tp.leaf_rec);
+    upload_array(h, R.leaf_id.data(), R.leaf_id.size() * 4, (void**)&tp.leaf_id);
+    upload_array(h, R.always.data(), R.always.size() * 4, (void**)&tp.always);
+    if (h->mode == MODE_BRUTE) upload_array(h, R.flat.data(), R.flat.size() * 4, (void**)&tp.filt);
+    upload_array(h, R.geo.data(), R.geo.size() * 8, (void**)&tp.geo);
+    upload_array(h, R.mat.data(), R.mat.size() * sizeof(DevMat), (void**)&tp.mat);
 
     std::vector<rtd::DevTex> texs(std::max<uint64_t>(s->n_textures, 1));
     for (uint64_t t = 0; t < s->n_textures; ++t) {
         const rt_image& im = s->textures[t];
         texs[t].rgb8 = nullptr; texs[t].width = im.width; texs[t].height = im.height;
-        if (im.rgb8 && im.width && im.height) {
-            if ((rc = upload_array(h, im.rgb8, im.width * im.height * 3, (void**)&texs[t].rgb8)) != RT_OK) return rc;
-        }
+        if (im.rgb8 && im.width && im.height && im.width * im.height * 3ull <= im.bytes)
+            upload_array(h, im.rgb8, im.width * im.height * 3, (void**)&texs[t].rgb8);
     }
-    if ((rc = upload_array(h, texs.data(), texs.size() * sizeof(rtd::DevTex), (void**)&tp.tex)) != RT_OK) return rc;
+    upload_array(h, texs.data(), texs.size() * sizeof(rtd::DevTex), (void**)&tp.tex);
     tp.sky_mode = s->sky.mode;
     tp.sky.rgb8 = nullptr; tp.sky.width = 0; tp.sky.height = 0;
     if (s->sky.mode == RT_SKY_TEXTURE) {
-        if ((rc = upload_array(h, s->sky.tex.rgb8, s->sky.tex.width * s->sky.tex.height * 3, (void**)&tp.sky.rgb8)) != RT_OK) return rc;
+        upload_array(h, s->sky.tex.rgb8, s->sky.tex.width * s->sky.tex.height * 3, (void**)&tp.sky.rgb8);
         tp.sky.width = s->sky.tex.width; tp.sky.height = s->sky.tex.height;
     }
-
     std::vector<uint32_t> lights;
     for (uint32_t i = 0; i < n; ++i) if (s->spheres[i].kind == RT_LIGHT) lights.push_back(i);
     lights.push_back(0);
-    if ((rc = upload_array(h, lights.data(), lights.size() * 4, (void**)&tp.lights)) != RT_OK) return rc;
-    tp.n = n; tp.n_pairs = n_pairs; tp.n_lights = n_lights;
-    tp.gx = g[0]; tp.gy = g[1]; tp.gz = g[2];
-    tp.er_coef = 1.0f - (float)(96.0 * U);
+    upload_array(h, lights.data(), lights.size() * 4, (void**)&tp.lights);
+    upload_array(h, nullptr, 16, (void**)&h->err);   // zero-filled error counters
+    tp.err = nullptr;                                // patched after commit
+    tp.gx = R.g[0]; tp.gy = R.g[1]; tp.gz = R.g[2];
+    tp.er_coef = 1.0f - (float)(96.0 * rtbvh::kU);
     tp.cam = s->camera;
     tp.width = s->width; tp.height = s->height; tp.spp = s->samples_per_pixel; tp.max_depth = s->max_depth;
     tp.key0 = (uint32_t)s->seed; tp.key1 = (uint32_t)(s->seed >> 32);
@@ -506,46 +390,34 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     tp.rows_local = rtb200_shard_rows(s->height, opts.rank, opts.world, opts.band_rows);
     tp.npix_local = tp.rows_local * s->width;
 
-    // ---- launch geometry: persistent grid = SMs x resident CTAs; scene fully in shared memory when it fits ----
-    if (h->lanes) {
-        size_t per_cta_budget = ctx->max_smem;   // opt-in max per block (227 KB)
-        size_t half_budget = (228 * 1024 - 2 * 1024 * kCtasPerSm) / kCtasPerSm;
-        size_t full_smem = trace_smem_bytes(n, n_pairs, true);
-        size_t filt_smem = trace_smem_bytes(n, n_pairs, false);
-        int ctas_per_sm = kCtasPerSm;
-        if (full_smem <= half_budget) { tp.scene_in_smem = 1; h->smem = full_smem; }
-        else if (filt_smem <= half_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; }
-        else if (full_smem <= per_cta_budget) { tp.scene_in_smem = 1; h->smem = full_smem; ctas_per_sm = 1; }
-        else if (filt_smem <= per_cta_budget) { tp.scene_in_smem = 0; h->smem = filt_smem; ctas_per_sm = 1; }
-        else return fail(RT_ERR_UNSUPPORTED, "RT_VARIANT_LANES: the sphere filter records exceed shared memory (use the default variant, which culls through cluster bounds)");
-        h->grid = ctx->sm_count * ctas_per_sm;
-    } else {
-        // What goes to shared memory besides the first-level filter records and the ray pool, in order of value:
-        // second-level sphere records (two-level mode), exact geometry (read by every f64 confirmation), materials
-        // (read once per hit). Pick the richest set that still leaves the targeted number of CTAs resident per SM.
-        // RTB200_WF_SMEM=<mask> overrides (bit0 sfilt, bit1 geo, bit2 mat) for tuning experiments.
+    // ---- launch geometry: persistent grid = SMs x resident CTAs. What goes to shared memory next to the ray pool, the
+    // per-ray constants and the work lists, in order of value: the hierarchy (read at every step), exact geometry (every f64
+    // test), materials (once per hit). The richest set that keeps the targeted residency wins; RTB200_WF_SMEM=<mask> overrides
+    // (bit0 hierarchy, bit1 geo, bit2 mat) and RTB200_WF_MINB=<2|3> pins the register budget, for tuning experiments.
+    {
         const char* es = getenv("RTB200_WF_SMEM");
+        const char* eb = getenv("RTB200_WF_MINB");
         const uint32_t masks[] = {7u, 3u, 1u, 0u};
         bool found = false;
-        // first choice: four resident CTAs per SM (kernel built for 64 registers); else the 128-register build at whatever fits
-        for (int minb : {4, 2}) {
+        for (int minb : {3, 2}) {
+            if (eb && atoi(eb) != minb) continue;
             for (int need : {minb, 1}) {
                 for (uint32_t mask : masks) {
                     if (found) break;
                     if (es && (uint32_t)atoi(es) != mask) continue;
-                    if (!two_level && (mask & 1u) && mask != 7u) continue;            // bit0 is meaningless without a second level
-                    size_t sm = wavefront_smem_bytes(n, n_pairs, n_clusters, two_level, mask, 256);
+                    if (h->mode == MODE_EXACT && (mask & 1u)) continue;
+                    size_t sm = wavefront_smem_bytes(tp, h->mode, mask);
                     if (sm > ctx->max_smem) continue;
-                    int occ = wavefront_max_ctas_per_sm(sm, minb);
+                    int occ = wavefront_max_ctas_per_sm(h->mode, n_lights > 0, sm, minb);
                     if (occ < need || occ <= 0) continue;
-                    h->block = 256; h->minb = minb; h->smem = sm; tp.scene_in_smem = mask; h->grid = ctx->sm_count * occ;
+                    h->minb = minb; h->smem = sm; tp.scene_in_smem = mask; h->ctas_per_sm = occ; h->grid = ctx->sm_count * occ;
                     found = true;
                 }
-                if (minb == 4) break;   // the 64-register build is only worth it at full residency
+                if (found || minb == 3) break;   // the 80-register build is only worth it at full residency
             }
             if (found) break;
         }
-        if (!found) return fail(RT_ERR_UNSUPPORTED, "first-level filter records exceed shared memory (needs a third level / streaming tiles)");
+        if (!found) return fail(RT_ERR_UNSUPPORTED, "no launch configuration fits shared memory");
     }
 
     // ---- per-sample staging: samples per batch bounded by the buffer cap ----
@@ -557,9 +429,37 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     h->spp_batch = (uint32_t)spb;
 
     if ((rc = commit_uploads(h)) != RT_OK) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));   // host staging vectors go out of scope
+    h->tp.err = h->err;
     guard.ok = true;
     *out = h;
+    return RT_OK;
+}
+
+int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
+    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rt_options opts;
+    int rc = normalise_options(opts_in, &opts);
+    if (rc != RT_OK) return rc;
+    uint32_t n_lights = 0;
+    if ((rc = validate_scene(s, &n_lights)) != RT_OK) return rc;
+    DeviceRestore restore;
+    rtbvh::Records R;
+    rtbvh::build_records(s, mode_of(opts.variant) == MODE_TREE, R);
+    return scene_upload_records(s, opts, n_lights, R, out);
+}
+
+int rtb200_scene_kernel_info(rtb200_scene_handle h, rt_kernel_info* out) {
+    if (!h || !out) return fail(RT_ERR_INVALID, "null argument");
+    DeviceRestore restore;
+    CU(cudaSetDevice(h->device));
+    memset(out, 0, sizeof *out);
+    KernelInfo ki{};
+    CU(wavefront_info(h->mode, h->tp.n_lights > 0, h->minb, &ki));
+    out->registers = ki.registers; out->local_bytes = ki.local_bytes; out->smem_bytes = (uint32_t)h->smem; out->grid = (uint32_t)h->grid; out->block = (uint32_t)kBlock;
+    out->ctas_per_sm = (uint32_t)h->ctas_per_sm; out->smem_mask = h->tp.scene_in_smem;
+    out->bvh_nodes = h->tp.n_nodes; out->bvh_leaves = h->tp.n_leaves; out->bvh_depth = h->tp.depth;
+    snprintf(out->name, sizeof out->name, "%s", ki.name);
     return RT_OK;
 }
 
@@ -570,6 +470,7 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
     DeviceCtx::WorkSet& W = ctx->ws[set & 1];
     CU(cudaSetDevice(h->device));
     cudaStream_t st = stream_in ? (cudaStream_t)stream_in : ctx->stream;
+    if (st != ctx->stream) CU(cudaStreamWaitEvent(st, ctx->staging_free, 0));   // the scene upload ran on the context's stream
     TraceParams tp = h->tp;
     h->last_stream = st; h->last_set = set & 1; h->last_batches = 0; h->last_launches = 0;
     if (h->n_streams < 2 && (h->n_streams == 0 || h->streams[0] != st)) h->streams[h->n_streams++] = st;
@@ -577,7 +478,7 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
 
     const uint32_t spp = tp.spp, spb = h->spp_batch;
     const uint32_t n_batches = (spp + spb - 1) / spb;
-    const uint32_t threads_total = (uint32_t)h->grid * (uint32_t)(h->lanes ? kBlock : h->block);
+    const uint32_t threads_total = (uint32_t)h->grid * (uint32_t)kBlock;
 
     CU(W.samplebuf.ensure((size_t)spb * tp.npix_local * 16));
     CU(W.accum.ensure((size_t)tp.npix_local * 12));
@@ -597,10 +498,10 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
     // event ring: every pending frame owns 2 + 2*n_batches events (begin, end, and a pair around each trace launch)
     const uint32_t kRing = 64, per_frame = 2 + 2 * n_batches;
     if (h->pending_frames >= kRing) return fail(RT_ERR_INVALID, "more than 64 frames enqueued without rtb200_render_device_wait");
-    while (ctx->ev.size() < (size_t)kRing * per_frame) {
-        cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e);
+    while (h->ev.size() < (size_t)(h->pending_frames + 1) * per_frame) {
+        cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev.push_back(e);
     }
-    cudaEvent_t* fev = ctx->ev.data() + (size_t)h->pending_frames * per_frame;
+    cudaEvent_t* fev = h->ev.data() + (size_t)h->pending_frames * per_frame;
     unsigned long long* stat = (unsigned long long*)W.small.p;
     unsigned int* counters = (unsigned int*)((char*)W.small.p + 256);
     CU(cudaMemsetAsync(W.small.p, 0, 256 + (size_t)n_batches * 4, st));
@@ -620,10 +521,8 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
         CU(cudaEventRecord(fev[2 + 2 * b], st));
         if (tp.max_depth == 0) {
             CU(cudaMemsetAsync(tp.samplebuf, 0, (size_t)tp.total_work * 16, st));   // ray_color(depth 0) = black, no ray (raytracer.rs:80-82)
-        } else if (h->lanes) {
-            CU(launch_trace(tp, h->grid, h->smem, false, st));
         } else {
-            CU(launch_wavefront(tp, h->grid, h->smem, h->minb, h->exact, st));
+            CU(launch_wavefront(tp, h->mode, h->grid, h->smem, h->minb, st));
         }
         CU(cudaEventRecord(fev[3 + 2 * b], st));
         ResolveParams q{};
@@ -639,47 +538,54 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
     return RT_OK;
 }
 
-// Wait for the most recently enqueued frame of `h` and fetch its statistics.
+// Wait for the frames of `h` enqueued so far and fetch statistics (counters: the last frame's; times: summed over the frames).
 static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
     if (!h) return fail(RT_ERR_INVALID, "null scene handle");
     DeviceCtx* ctx = h->ctx;
     CU(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof *stats);
-    if (h->tp.npix_local == 0 || h->last_batches == 0 || h->pending_frames == 0) return RT_OK;
+    if (h->tp.npix_local == 0 || h->last_batches == 0 || h->pending_frames == 0) { h->pending_frames = 0; h->n_streams = 0; return RT_OK; }
     cudaStream_t st = h->last_stream;
     DeviceCtx::WorkSet& W = ctx->ws[h->last_set];
-    unsigned long long hstat[16] = {0};
+    unsigned long long hstat[16] = {0}, herr[2] = {0, 0};
     CU(cudaMemcpyAsync(hstat, W.small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
     for (int i = 0; i < h->n_streams; ++i) CU(cudaStreamSynchronize(h->streams[i]));
     h->n_streams = 0;
-    if (hstat[5] != 0) { h->pending_frames = 0; }
-    if (hstat[5] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred; the frame is not exact (the reference recursion is near-critical for this many lights)");
+    // error counters accumulate over every frame since the last wait (each frame ORs into them; nothing clears them in between)
+    CU(cudaMemcpy(herr, h->err, sizeof herr, cudaMemcpyDeviceToHost));
+    if (herr[0] | herr[1]) CU(cudaMemset(h->err, 0, sizeof herr));
+    const uint32_t frames = h->pending_frames;
+    h->pending_frames = 0;
+    if (herr[1] != 0) return fail(RT_ERR_CUDA, "internal error: the traversal guard tripped; the frame is not valid");
+    if (herr[0] != 0) return fail(RT_ERR_UNSUPPORTED, "light-test recursion deeper than the shadow-frame stack occurred in one of the frames; it is not exact (the reference recursion is near-critical for this many lights)");
     if (stats) {
-        // device_ms / trace_ms: summed over every frame enqueued since the previous wait; the counters are the last frame's
         float ms = 0.f;
         double dv = 0.0, tr = 0.0;
         const uint32_t per_frame = 2 + 2 * h->last_batches;
-        for (uint32_t f = 0; f < h->pending_frames; ++f) {
-            cudaEvent_t* fev = ctx->ev.data() + (size_t)f * per_frame;
+        for (uint32_t f = 0; f < frames; ++f) {
+            cudaEvent_t* fev = h->ev.data() + (size_t)f * per_frame;
             CU(cudaEventElapsedTime(&ms, fev[0], fev[1])); dv += ms;
             for (uint32_t b = 0; b < h->last_batches; ++b) { CU(cudaEventElapsedTime(&ms, fev[2 + 2 * b], fev[3 + 2 * b])); tr += ms; }
         }
-        stats->device_ms = dv; stats->trace_ms = tr; stats->frames = h->pending_frames;
-        stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4];
+        stats->device_ms = dv; stats->trace_ms = tr; stats->frames = frames;
+        stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4]; stats->nodes = hstat[6];
+        stats->gpus_used = 1;
         if (getenv("RTB200_PRINT_PHASES")) {
-            fprintf(stderr, "[rtb200] stage_mismatch=%llu ovf=%llu phases(warp-cycles): scan=%llu confirm=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
-                    hstat[6], hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
+            fprintf(stderr, "[rtb200] fallbacks=%llu phases(warp-cycles): traverse=%llu exact=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
+                    hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
         }
         if (h->tp.max_depth == 0) stats->samples = (uint64_t)h->tp.npix_local * h->tp.spp;   // no kernel ran: every sample is black
-        stats->kernel_launches = h->last_launches * h->pending_frames; stats->batches = h->last_batches;
+        stats->kernel_launches = h->last_launches * frames; stats->batches = h->last_batches;
     }
-    h->pending_frames = 0;
     return RT_OK;
 }
 
 int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in, rt_stats* stats) {
+    if (!h) return fail(RT_ERR_INVALID, "null scene handle");
     auto wall0 = std::chrono::steady_clock::now();
-    if (h && h->pending_frames) { int rcw = render_collect(h, nullptr); if (rcw != RT_OK) return rcw; }   // drain frames enqueued earlier
+    DeviceRestore restore;
+    std::lock_guard<std::recursive_mutex> lk(h->ctx->mu);
+    if (h->pending_frames) { int rcw = render_collect(h, nullptr); if (rcw != RT_OK) return rcw; }   // drain frames enqueued earlier
     int rc = render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in, 0);
     if (rc != RT_OK) return rc;
     rc = render_collect(h, stats);
@@ -689,17 +595,27 @@ int rtb200_render_device(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear
 
 int rtb200_render_device_async(rtb200_scene_handle h, void* dev_rgb8, void* dev_linear_f32, void* stream_in) {
     if (!h) return fail(RT_ERR_INVALID, "null scene handle");
+    DeviceRestore restore;
+    std::lock_guard<std::recursive_mutex> lk(h->ctx->mu);
     return render_enqueue(h, dev_rgb8, dev_linear_f32, stream_in, (int)(h->frame_counter++ & 1u));
 }
 
-int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats) { return render_collect(h, stats); }
+int rtb200_render_device_wait(rtb200_scene_handle h, rt_stats* stats) {
+    if (!h) return fail(RT_ERR_INVALID, "null scene handle");
+    DeviceRestore restore;
+    std::lock_guard<std::recursive_mutex> lk(h->ctx->mu);
+    return render_collect(h, stats);
+}
 
 static int render_host(const rt_scene* s, const rt_options* opts, uint8_t* out_rgb8, float* out_lin, rt_stats* stats) {
     auto wall0 = std::chrono::steady_clock::now();
+    DeviceRestore restore;
     rtb200_scene_handle h = nullptr;
     int rc = rtb200_scene_upload(s, opts, &h);
     if (rc != RT_OK) return rc;
     DeviceCtx* ctx = h->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaSetDevice(h->device);
     size_t npl = h->tp.npix_local;
     void *d8 = nullptr, *dl = nullptr;
     cudaError_t e = cudaSuccess;
@@ -715,8 +631,10 @@ static int render_host(const rt_scene* s, const rt_options* opts, uint8_t* out_r
         if (e != cudaSuccess) rc = fail_cuda(e, "device->host copy of the frame");
     }
     st.h2d_bytes = h->h2d_bytes;
-    st.d2h_bytes = (out_rgb8 ? npl * 3 : 0) + (out_lin ? npl * 12 : 0) + 32;
+    st.d2h_bytes = (out_rgb8 ? npl * 3 : 0) + (out_lin ? npl * 12 : 0) + 128 + 16;
+    std::string keep = g_last_error;
     rtb200_scene_release(h);
+    if (rc != RT_OK) g_last_error = keep;
     st.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     if (stats) *stats = st;
     return rc;
@@ -729,6 +647,86 @@ int rtb200_render_rgb8(const rt_scene* scene, const rt_options* opts, uint8_t* o
 int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, float* out_rgb, rt_stats* stats) {
     if (!scene || !out_rgb) return fail(RT_ERR_INVALID, "null argument");
     return render_host(scene, opts, nullptr, out_rgb, stats);
+}
+
+// One process, n_gpus devices: the reference's row bands (raytracer.rs:254-262) dealt round-robin to the devices (band b ->
+// device b mod G, like the torchrun flavour in rtb200/dist.py), every device renders its compact shard, the shards are
+// copied peer-to-peer over NVLink straight into their interleaved rows of the frame on device 0, ONE device->host copy.
+int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32_t n_gpus, uint8_t* out_rgb8, rt_stats* stats) {
+    if (!s || !out_rgb8) return fail(RT_ERR_INVALID, "null argument");
+    auto wall0 = std::chrono::steady_clock::now();
+    rt_options base;
+    int rc = normalise_options(opts_in, &base);
+    if (rc != RT_OK) return rc;
+    if (base.world != 1 || base.rank != 0) return fail(RT_ERR_INVALID, "rtb200_render_rgb8_multi shards the frame itself: opts->rank/world must be 0/1");
+    uint32_t n_lights = 0;
+    if ((rc = validate_scene(s, &n_lights)) != RT_OK) return rc;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (count <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device");
+    const int first = base.device < 0 ? 0 : base.device;
+    if (first >= count) return fail(RT_ERR_NO_DEVICE, "no such CUDA device");
+    int G = n_gpus <= 0 ? count - first : std::min(n_gpus, count - first);
+    const uint32_t bands = (s->height + base.band_rows - 1) / base.band_rows;
+    G = (int)std::min<uint32_t>((uint32_t)G, bands);
+    if (G <= 1) { base.device = first; int r = render_host(s, &base, out_rgb8, nullptr, stats); if (r == RT_OK && stats) stats->gpus_used = 1; return r; }
+
+    DeviceRestore restore;
+    rtbvh::Records R;
+    rtbvh::build_records(s, mode_of(base.variant) == MODE_TREE, R);
+    std::vector<rtb200_scene_handle> hs((size_t)G, nullptr);
+    std::vector<std::unique_lock<std::recursive_mutex>> locks;
+    struct Cleanup { std::vector<rtb200_scene_handle>& v; ~Cleanup() { std::string keep = g_last_error; for (auto h : v) if (h) rtb200_scene_release(h); g_last_error = keep; } } cleanup{hs};
+    const size_t row_bytes = (size_t)s->width * 3;
+    for (int g = 0; g < G; ++g) {            // ascending device order: two concurrent multi-GPU calls cannot deadlock
+        rt_options o = base; o.device = first + g; o.rank = g; o.world = G;
+        if ((rc = scene_upload_records(s, o, n_lights, R, &hs[g])) != RT_OK) return rc;
+        locks.emplace_back(hs[g]->ctx->mu);
+    }
+    DeviceCtx* c0 = hs[0]->ctx;
+    CU(cudaSetDevice(first));
+    CU(c0->frame.ensure((size_t)s->height * row_bytes + 16));
+    uint8_t* frame = (uint8_t*)c0->frame.p;
+    for (int g = 1; g < G; ++g) {            // peer access both ways (already-enabled is fine; without it the copies stage through the host)
+        cudaSetDevice(first); if (cudaDeviceEnablePeerAccess(first + g, 0) != cudaSuccess) cudaGetLastError();
+        cudaSetDevice(first + g); if (cudaDeviceEnablePeerAccess(first, 0) != cudaSuccess) cudaGetLastError();
+    }
+    std::vector<cudaEvent_t> done((size_t)G, nullptr);
+    struct EvCleanup { std::vector<cudaEvent_t>& v; int first; ~EvCleanup() { for (size_t g = 0; g < v.size(); ++g) if (v[g]) { cudaSetDevice(first + (int)g); cudaEventDestroy(v[g]); } } } evc{done, first};
+    for (int g = 0; g < G; ++g) {
+        DeviceCtx* c = hs[g]->ctx;
+        CU(cudaSetDevice(first + g));
+        const size_t rows = hs[g]->tp.rows_local;
+        CU(c->out_rgb8.ensure(rows * row_bytes + 16));
+        if ((rc = render_enqueue(hs[g], c->out_rgb8.p, nullptr, nullptr, 0)) != RT_OK) return rc;
+        // shard -> frame: full bands as one strided 2-D copy (a "row" of the copy = one band), then the partial last band
+        const size_t band_bytes = (size_t)base.band_rows * row_bytes;
+        const size_t full = rows / base.band_rows, rem = rows - full * base.band_rows;
+        if (full) CU(cudaMemcpy2DAsync(frame + (size_t)g * band_bytes, (size_t)G * band_bytes, c->out_rgb8.p, band_bytes, band_bytes, full, cudaMemcpyDefault, c->stream));
+        if (rem) CU(cudaMemcpyAsync(frame + ((size_t)full * G + g) * band_bytes, (uint8_t*)c->out_rgb8.p + full * band_bytes, rem * row_bytes, cudaMemcpyDefault, c->stream));
+        CU(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
+        CU(cudaEventRecord(done[g], c->stream));
+    }
+    CU(cudaSetDevice(first));
+    for (int g = 1; g < G; ++g) CU(cudaStreamWaitEvent(c0->stream, done[g], 0));
+    CU(cudaMemcpyAsync(out_rgb8, frame, (size_t)s->height * row_bytes, cudaMemcpyDeviceToHost, c0->stream));
+    rt_stats total{};
+    for (int g = 0; g < G; ++g) {
+        rt_stats st{};
+        if ((rc = render_collect(hs[g], &st)) != RT_OK) return rc;
+        total.rays += st.rays; total.samples += st.samples; total.candidates += st.candidates; total.clusters += st.clusters; total.nodes += st.nodes;
+        total.device_ms = std::max(total.device_ms, st.device_ms); total.trace_ms = std::max(total.trace_ms, st.trace_ms);
+        total.kernel_launches += st.kernel_launches; total.batches = std::max(total.batches, st.batches);
+        total.h2d_bytes += hs[g]->h2d_bytes;
+    }
+    CU(cudaSetDevice(first));
+    CU(cudaStreamSynchronize(c0->stream));
+    total.frames = 1; total.gpus_used = G;
+    total.d2h_bytes = (size_t)s->height * row_bytes + (size_t)G * (128 + 16);
+    total.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (stats) *stats = total;
+    return RT_OK;
 }
 
 // ---- probes ------------------------------------------------------------------------------------------

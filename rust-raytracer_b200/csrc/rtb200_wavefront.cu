@@ -1,13 +1,18 @@
 // rtb200_wavefront.cu — the production trace kernel: a persistent-threads WAVEFRONT tracer at CTA scope.
 //
-// One persistent CTA (256 threads) per resident slot of every SM owns a pool of 256 ray slots in shared memory,
-// laid out SoA, next to the scene's sphere/material records (staged once by 1-D TMA bulk copies). Until the global
-// (pixel,sample) queue is drained and the pool is empty, the CTA repeats three barrier-separated stages:
+// One persistent CTA (256 threads) per resident slot of every SM owns a pool of 256 ray slots in shared memory, laid
+// out SoA (the scene's hierarchy / sphere / material records are staged next to it by 1-D TMA bulk copies when they
+// fit). Until the global (pixel,sample) queue is drained and the pool is empty, the CTA repeats three stages:
 //
-//   closest-hit   thread t <-> slot t. hit_world (raytracer.rs:44-59) over ALL spheres as a conservative f32 filter
-//                 (7 FMA per sphere, two spheres per packed FFMA2, blocks of 8 spheres without a branch) that appends
-//                 candidates to a per-thread list, then the reference-exact f64 Sphere::hit (sphere.rs:46-78) on the
-//                 candidates only (ascending index: ties go to the first sphere like raytracer.rs:52-56).
+//   closest-hit   hit_world (raytracer.rs:44-59) as a WARP-COOPERATIVE traversal of an 8-wide BVH. Each warp owns the
+//                 32 rays of its slots and three work lists in shared memory: (ray, node) pairs, (ray, leaf) pairs and
+//                 (ray, sphere) candidates. A step pops up to 32 pairs, ONE PER LANE, whatever ray they belong to:
+//                   node step   8 conservative f32 slab tests (FFMA2 + FMNMX3), children pushed by a warp prefix sum;
+//                   leaf step   the 7-FMA conservative sphere test on the leaf's 4 spheres (two per packed FFMA2);
+//                   exact step  the reference-exact f64 Sphere::hit (sphere.rs:46-78) on a candidate; the per-ray result
+//                               is the lexicographic minimum of (root, ORIGINAL sphere index) - equal to hit_world's
+//                               fold with its strict '<' (first sphere wins ties) whatever the visiting order.
+//                 So 32 lanes do 32 tests at every level, however unevenly the work is spread over the rays.
 //   sort          rays are classified {miss, diffuse, metal, glass, light} and compacted class by class with warp
 //                 ballots + one shared-memory atomic per (warp, class): perm[] lists the live slots sorted by class.
 //   shade+ray-gen thread i <-> slot perm[i], so a warp shades ONE material: Material::scatter (materials.rs:44-54) or
@@ -16,20 +21,14 @@
 //                 recursion (raytracer.rs:117-122). A terminated path writes its sample and the same thread
 //                 immediately regenerates the slot from the queue (render_line's jitter + Camera::get_ray,
 //                 raytracer.rs:199-201): one warp-aggregated atomic pops the work items.
-//
-// FMA-pipe work (closest-hit) of one CTA overlaps FP64-pipe work (shade) of the other CTAs resident on the SM.
+#include <cstdio>
+
 #include "rtb200_kernels.cuh"
 
 using namespace rtd;
 
-#ifndef RT_L1_GUARD
-#define RT_L1_GUARD 0
-#endif
 #ifndef RT_SAMPLE_ILP
 #define RT_SAMPLE_ILP 1   // two rejection trials per trip with their Philox blocks computed together (bit-identical stream)
-#endif
-#ifndef RT_CONFIRM_ILP
-#define RT_CONFIRM_ILP 0   // two candidates per trip with interleaved f64 chains: bit-identical, but measured 5 % SLOWER (wasted sqrt/div on misses)
 #endif
 #ifndef RT_SMEM_STACK
 #define RT_SMEM_STACK 3   // albedo-stack levels kept in shared memory per slot (deeper levels live in global memory)
@@ -41,32 +40,37 @@ namespace {
 
 enum : uint32_t { CLS_MISS = 0, CLS_DIFFUSE = 1, CLS_METAL = 2, CLS_GLASS = 3, CLS_LIGHT = 4, CLS_DEAD = 5, N_CLS = 6 };
 constexpr uint32_t kDeadLevel = 0xffffffffu;
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr unsigned long long kNoHitBits = 0x7ff0000000000000ull;   // +inf as the "no root yet" key (roots are > t_min > 0)
 
 struct WfSmem {
-    uint32_t filt_off, sfilt_off, orig_off, cmeta_off, geo_off, mat_off, l1_off, l2_off;
-    uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each
+    uint32_t nodes_off, leafrec_off, leafid_off, filt_off, geo_off, mat_off;
+    uint32_t cA, cB, cC;                            // float4[kBlock] each: per-ray f32 constants of the conservative tests
+    uint32_t lists;                                 // uint32[warps][kCapIn + kCapLf + kCapCd]
+    uint32_t ox, oy, oz, dx, dy, dz, bt;            // double[kBlock] each (bt: best root, updated as u64 bits)
     uint32_t bi, work, pix, smp, blk, clo, chi, lvl, shd;   // uint32[kBlock] each
     uint32_t perm;                                  // uint16[kBlock]
     uint32_t stk;                                   // uint32[RT_SMEM_STACK][kBlock]: first levels of the albedo stack
     uint32_t cnt;                                   // uint32[2][8]
-    uint32_t flags;                                 // uint32[4]
     uint32_t total;
 };
 
-// mask: bit0 second-level sphere records (+slot map), bit1 exact geometry, bit2 materials in shared memory
-__host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t mask, uint32_t kBlock) {
+// mask: bit0 hierarchy (MODE_TREE) / flat records (MODE_BRUTE), bit1 exact geometry, bit2 materials in shared memory
+__host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32_t n_nodes, uint32_t n_leaves, uint32_t mode, uint32_t mask) {
     WfSmem L;
     uint32_t off = 16;   // mbarrier
-    L.filt_off = off; off += n_pairs * 32u;
-    L.sfilt_off = off; if (two_level && (mask & 1u)) off += n_clusters * (uint32_t)(kClusterK * 16);
-    L.orig_off = off; if (two_level && (mask & 1u)) off += n_clusters * (uint32_t)(kClusterK * 2);
-    L.cmeta_off = off; if (two_level && (mask & 1u)) off += n_clusters * 4u;
-    off = (off + 15u) & ~15u;
+    L.nodes_off = off;   if (mode == MODE_TREE && (mask & 1u)) off += n_nodes * (uint32_t)(kNodeVec * 16);
+    L.leafrec_off = off; if (mode == MODE_TREE && (mask & 1u)) off += n_leaves * (uint32_t)(kLeafK * 16);
+    L.leafid_off = off;  if (mode == MODE_TREE && (mask & 1u)) off += n_leaves * (uint32_t)(kLeafK * 4);
+    L.filt_off = off;    if (mode == MODE_BRUTE && (mask & 1u)) off += n_pairs * 32u;
     L.geo_off = off; if (mask & 2u) off += n * 32u;
     L.mat_off = off; if (mask & 4u) off += n * 32u;
-    L.l1_off = off; off += (uint32_t)kWfMaxClus * kBlock * 2u;
-    L.l2_off = off; if (two_level) off += (uint32_t)kWfMaxCand * kBlock * 2u;
     off = (off + 15u) & ~15u;
+    L.cA = off; L.cB = off; L.cC = off; L.lists = off;
+    if (mode == MODE_TREE) {
+        L.cA = off; off += kBlock * 16u; L.cB = off; off += kBlock * 16u; L.cC = off; off += kBlock * 16u;
+        L.lists = off; off += (uint32_t)(kBlock / 32) * (uint32_t)(kCapIn + kCapLf + kCapCd) * 4u;
+    }
     L.ox = off; off += kBlock * 8u; L.oy = off; off += kBlock * 8u; L.oz = off; off += kBlock * 8u;
     L.dx = off; off += kBlock * 8u; L.dy = off; off += kBlock * 8u; L.dz = off; off += kBlock * 8u;
     L.bt = off; off += kBlock * 8u;
@@ -75,7 +79,6 @@ __host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32
     L.perm = off; off += kBlock * 2u;
     L.stk = off; off += (uint32_t)RT_SMEM_STACK * kBlock * 4u;
     L.cnt = off; off += 2u * 8u * 4u;
-    L.flags = off; off += 16u;
     L.total = off;
     return L;
 }
@@ -100,29 +103,60 @@ RT_DEV void albedo_of(uint32_t code, const DevMat* mat, float& r, float& g, floa
     }
 }
 
-}  // namespace
+RT_DEV float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+RT_DEV float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
-size_t wavefront_smem_bytes(uint32_t n, uint32_t n_pairs, uint32_t n_clusters, bool two_level, uint32_t smem_mask, int block) {
-    return wf_layout(n, n_pairs, n_clusters, two_level, smem_mask, (uint32_t)block).total;
+// inclusive warp prefix sum of a packed pair of 16-bit counters
+RT_DEV uint32_t warp_scan_incl(uint32_t v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
 }
 
-template <int kBlock, int MINB, bool EXACT, bool LIGHTS, bool TWO>
+// the 7-FMA conservative sphere test on NP pair-packed records: D = (c.d^ - o.d^)^2 + 2 c.o + nk   (candidate iff D >= thr)
+#define RT_FILTER_PAIRS(REC, DV, NP)                                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < (NP); ++q) {                                                                              \
+        float4 A_ = (REC)[2 * q], B_ = (REC)[2 * q + 1];                                                                             \
+        float2 cx = make_float2(A_.x, A_.y), cy = make_float2(A_.z, A_.w), cz = make_float2(B_.x, B_.y), nk = make_float2(B_.z, B_.w); \
+        float2 bb = __ffma2_rn(cz, dz2, nod2);                                                                                       \
+        float2 tt = __ffma2_rn(cz, oz2, nk);                                                                                         \
+        bb = __ffma2_rn(cy, dy2, bb);                                                                                                \
+        tt = __ffma2_rn(cy, oy2, tt);                                                                                                \
+        bb = __ffma2_rn(cx, dx2, bb);                                                                                                \
+        tt = __ffma2_rn(cx, ox2, tt);                                                                                                \
+        (DV)[q] = __ffma2_rn(bb, bb, tt);                                                                                            \
+    }
+
+}  // namespace
+
+size_t wavefront_smem_bytes(const TraceParams& p, uint32_t mode, uint32_t smem_mask) {
+    return wf_layout(p.n, p.n_pairs, p.n_nodes, p.n_leaves, mode, smem_mask).total;
+}
+
+template <int MINB, uint32_t MODE, bool LIGHTS>
 __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid_constant__ TraceParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const WfSmem L = wf_layout(p.n, p.n_pairs, p.n_clusters, TWO, p.scene_in_smem, kBlock);
+    const WfSmem L = wf_layout(p.n, p.n_pairs, p.n_nodes, p.n_leaves, MODE, p.scene_in_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    const float4* s_filt = reinterpret_cast<const float4*>(smem_raw + L.filt_off);
-    uint16_t* s_l1 = reinterpret_cast<uint16_t*>(smem_raw + L.l1_off);     // first-level candidates (clusters, or spheres without clustering)
-    uint16_t* s_l2 = reinterpret_cast<uint16_t*>(smem_raw + L.l2_off);     // second-level candidates (spheres), two-level mode
-    const float4* sfilt = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const float4*>(smem_raw + L.sfilt_off) : p.sfilt;
-    const uint16_t* orig = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const uint16_t*>(smem_raw + L.orig_off) : p.orig;
-    const float* cmeta = (TWO && (p.scene_in_smem & 1u)) ? reinterpret_cast<const float*>(smem_raw + L.cmeta_off) : p.cmeta;   // |c| of each cluster bound
+    const bool tree_smem = (p.scene_in_smem & 1u) != 0u;
+    const float4* nodes = (MODE == MODE_TREE && tree_smem) ? reinterpret_cast<const float4*>(smem_raw + L.nodes_off) : p.nodes;
+    const float4* leaf_rec = (MODE == MODE_TREE && tree_smem) ? reinterpret_cast<const float4*>(smem_raw + L.leafrec_off) : p.leaf_rec;
+    const uint32_t* leaf_id = (MODE == MODE_TREE && tree_smem) ? reinterpret_cast<const uint32_t*>(smem_raw + L.leafid_off) : p.leaf_id;
+    const float4* s_filt = (MODE == MODE_BRUTE && tree_smem) ? reinterpret_cast<const float4*>(smem_raw + L.filt_off) : p.filt;
     const double4* geo = (p.scene_in_smem & 2u) ? reinterpret_cast<const double4*>(smem_raw + L.geo_off) : p.geo;
     const DevMat* mat = (p.scene_in_smem & 4u) ? reinterpret_cast<const DevMat*>(smem_raw + L.mat_off) : p.mat;
+    float4* s_cA = reinterpret_cast<float4*>(smem_raw + L.cA);   // {o.x, o.y, o.z, m_ray}   recentred f32 origin, slab margin
+    float4* s_cB = reinterpret_cast<float4*>(smem_raw + L.cB);   // {1/d^.x, 1/d^.y, 1/d^.z, thr}
+    float4* s_cC = reinterpret_cast<float4*>(smem_raw + L.cC);   // {d^.x, d^.y, d^.z, -o.d^}
+    uint32_t* s_lists = reinterpret_cast<uint32_t*>(smem_raw + L.lists);
     double* s_ox = reinterpret_cast<double*>(smem_raw + L.ox); double* s_oy = reinterpret_cast<double*>(smem_raw + L.oy);
     double* s_oz = reinterpret_cast<double*>(smem_raw + L.oz); double* s_dx = reinterpret_cast<double*>(smem_raw + L.dx);
     double* s_dy = reinterpret_cast<double*>(smem_raw + L.dy); double* s_dz = reinterpret_cast<double*>(smem_raw + L.dz);
     double* s_bt = reinterpret_cast<double*>(smem_raw + L.bt);
+    unsigned long long* s_btu = reinterpret_cast<unsigned long long*>(smem_raw + L.bt);
     uint32_t* s_bi = reinterpret_cast<uint32_t*>(smem_raw + L.bi); uint32_t* s_work = reinterpret_cast<uint32_t*>(smem_raw + L.work);
     uint32_t* s_pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix); uint32_t* s_smp = reinterpret_cast<uint32_t*>(smem_raw + L.smp);
     uint32_t* s_blk = reinterpret_cast<uint32_t*>(smem_raw + L.blk); uint32_t* s_clo = reinterpret_cast<uint32_t*>(smem_raw + L.clo);
@@ -131,7 +165,6 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
     uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem_raw + L.perm);
     uint32_t* s_stk = reinterpret_cast<uint32_t*>(smem_raw + L.stk);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_raw + L.cnt);
-    volatile uint32_t* s_flags = reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags);   // [0] = queue exhausted
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -148,36 +181,27 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
     // ---- stage the scene into shared memory (TMA bulk copies, one mbarrier) ----
     if (tid == 0) mbar_init(bar, 1);
     if (tid < 16) s_cnt[tid] = 0;
-    if (tid < 4) s_flags[tid] = 0;
     s_lvl[tid] = kDeadLevel;
     __syncthreads();
     if (tid == 0) {
-        const bool sf = TWO && (p.scene_in_smem & 1u);
-        uint32_t bytes = p.n_pairs * 32u + (sf ? p.n_clusters * (uint32_t)(kClusterK * 18 + 4) : 0u) + ((p.scene_in_smem & 2u) ? p.n * 32u : 0u) + ((p.scene_in_smem & 4u) ? p.n * 32u : 0u);
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_stage(smem_raw + L.filt_off, p.filt, p.n_pairs * 32u, bar);
-        if (sf) {
-            bulk_stage(smem_raw + L.sfilt_off, p.sfilt, p.n_clusters * (uint32_t)(kClusterK * 16), bar);
-            bulk_stage(smem_raw + L.orig_off, p.orig, p.n_clusters * (uint32_t)(kClusterK * 2), bar);
-            bulk_stage(smem_raw + L.cmeta_off, p.cmeta, p.n_clusters * 4u, bar);
-        }
-        if (p.scene_in_smem & 2u) bulk_stage(smem_raw + L.geo_off, p.geo, p.n * 32u, bar);
-        if (p.scene_in_smem & 4u) bulk_stage(smem_raw + L.mat_off, p.mat, p.n * 32u, bar);
+        const uint32_t b_nodes = (MODE == MODE_TREE && tree_smem) ? p.n_nodes * (uint32_t)(kNodeVec * 16) : 0u;
+        const uint32_t b_lrec = (MODE == MODE_TREE && tree_smem) ? p.n_leaves * (uint32_t)(kLeafK * 16) : 0u;
+        const uint32_t b_lid = (MODE == MODE_TREE && tree_smem) ? p.n_leaves * (uint32_t)(kLeafK * 4) : 0u;
+        const uint32_t b_filt = (MODE == MODE_BRUTE && tree_smem) ? p.n_pairs * 32u : 0u;
+        const uint32_t b_geo = (p.scene_in_smem & 2u) ? p.n * 32u : 0u, b_mat = (p.scene_in_smem & 4u) ? p.n * 32u : 0u;
+        mbar_arrive_expect_tx(bar, b_nodes + b_lrec + b_lid + b_filt + b_geo + b_mat);
+        if (b_nodes) bulk_stage(smem_raw + L.nodes_off, p.nodes, b_nodes, bar);
+        if (b_lrec) bulk_stage(smem_raw + L.leafrec_off, p.leaf_rec, b_lrec, bar);
+        if (b_lid) bulk_stage(smem_raw + L.leafid_off, p.leaf_id, b_lid, bar);
+        if (b_filt) bulk_stage(smem_raw + L.filt_off, p.filt, b_filt, bar);
+        if (b_geo) bulk_stage(smem_raw + L.geo_off, p.geo, b_geo, bar);
+        if (b_mat) bulk_stage(smem_raw + L.mat_off, p.mat, b_mat, bar);
     }
     mbar_wait(bar, 0);
-#ifdef RT_DEBUG_STAGE
-    {   // verify the TMA staging of the first-level records against global memory
-        unsigned long long bad = 0;
-        const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(p.filt);
-        const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(smem_raw + L.filt_off);
-        for (uint32_t i = tid; i < p.n_pairs * 8u; i += kBlock) if (gsrc[i] != ssrc[i]) ++bad;
-        if (bad) atomicAdd(&p.stat[6], bad);
-    }
-#endif
 
-    unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0, st_clus = 0;
+    unsigned long long st_rays = 0, st_cand = 0, st_ovf = 0, st_samples = 0, st_leaves = 0, st_nodes = 0;
 #ifdef RT_PROFILE_PHASES
-    unsigned long long pf_scan = 0, pf_confirm = 0, pf_waitA = 0, pf_sort = 0, pf_shade = 0, pf_waitC = 0, pf_iters = 0, pf_t = clock64();
+    unsigned long long pf_trav = 0, pf_exact = 0, pf_waitA = 0, pf_sort = 0, pf_shade = 0, pf_waitC = 0, pf_iters = 0, pf_t = clock64();
 #define PF_MARK(acc) { unsigned long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; }
 #else
 #define PF_MARK(acc)
@@ -185,17 +209,19 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
 
     // Regenerate slot `s` from the global (pixel,sample) queue. Warp-synchronous: every lane of the warp calls it,
     // `want` says whether this lane's slot needs a new path. raytracer.rs:199-201 + camera.rs:79-84.
+    bool exhausted = false;   // warp-uniform: this warp has seen the end of the queue
     auto regenerate = [&](bool want, uint32_t s) {
-        want = want && (s_flags[0] == 0u);
+        want = want && !exhausted;
         unsigned need = __ballot_sync(FULL, want);
         if (!need) return;
         int leader = __ffs(need) - 1;
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(p.work_counter, (unsigned)__popc(need));
         base = __shfl_sync(FULL, base, leader);
+        if (base + (unsigned)__popc(need) >= p.total_work) exhausted = true;
         if (!want) return;
         unsigned my = base + __popc(need & ((1u << lane) - 1u));
-        if (my >= p.total_work) { s_flags[0] = 1u; return; }
+        if (my >= p.total_work) return;
         uint32_t s_local = my / p.npix_local;
         uint32_t lp = my - s_local * p.npix_local;
         uint32_t y_local = lp / p.width, x = lp - y_local * p.width;
@@ -222,23 +248,32 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
     regenerate(true, (uint32_t)tid);   // initial fill of the pool
     __syncthreads();
 
+    const uint32_t wbase = (uint32_t)(tid & ~31);                      // first slot of this warp
+    uint32_t* wl_in = s_lists + (uint32_t)(tid >> 5) * (uint32_t)(kCapIn + kCapLf + kCapCd);
+    uint32_t* wl_lf = wl_in + kCapIn;
+    uint32_t* wl_cd = wl_lf + kCapLf;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // LIFO reserve: single-entry descents grow the node stack by at most 7 per level, so multi-entry steps may fill it only
+    // up to fat_in; above that the stack is popped one entry at a time and can never overflow.
+    const uint32_t fat_in = (uint32_t)kCapIn - 7u * p.depth - 8u;
+
     uint32_t it = 0;
     for (;; ++it) {
         uint32_t* cnt = s_cnt + (it & 1u) * 8u;
-        // =========================== closest-hit: thread t <-> slot t ===========================
+        // =========================== closest-hit ===========================
         const bool alive = s_lvl[tid] != kDeadLevel;
         uint32_t cls = CLS_DEAD;
-        {
+        if (__ballot_sync(FULL, alive) != 0u) {   // a warp whose 32 slots are all empty skips the stage (frame tail)
             const D3 o = mk(s_ox[tid], s_oy[tid], s_oz[tid]), d = mk(s_dx[tid], s_dy[tid], s_dz[tid]);
-            bool ovf = false;
             const double a = length_squared(d);
-            // exact f64 confirmation. hit_world (raytracer.rs:44-59) keeps the closest root and, on equal t, the first sphere in
-            // list order; because Sphere::hit(t_max) accepts exactly r < t_max with r the first root beyond t_min, that fold equals
-            // the lexicographic minimum of (r, index) over all spheres - so candidates may be confirmed in any order.
+            bool ovf = false;
+            // thread-private exact f64 confirmation (fallback paths: every sphere / the always-list / MODE_BRUTE candidates).
+            // hit_world (raytracer.rs:44-59) keeps the closest root and, on equal t, the first sphere in list order; because
+            // Sphere::hit(t_max) accepts exactly r < t_max with r the first root beyond t_min, that fold equals the lexicographic
+            // minimum of (r, index) over all spheres - so candidates may be confirmed in any order.
             double best_t = DBL_MAX;
             int best = -1;
             auto confirm = [&](int j) {
-                if (j >= (int)p.n) return;   // padding record
                 double4 gq = geo[j];
                 double root;
                 if (sphere_root(mk(gq.x, gq.y, gq.z), gq.w, o, d, a, 0.001, DBL_MAX, root)) {
@@ -246,175 +281,229 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
                 }
                 ++st_cand;
             };
-            auto consider = [&](int j, bool hit, double root) {
-                if (hit && (best < 0 || root < best_t || (root == best_t && j < best))) { best_t = root; best = j; }
-            };
-            // the candidates of a list, two at a time (interleaved f64 chains), then the odd one
-            auto confirm_list = [&](const uint16_t* cl, int cnt) {
-                int j = 0;
-                if (RT_CONFIRM_ILP) {
-                    for (; j + 1 < cnt; j += 2) {
-                        const int j0 = (int)cl[j * kBlock + tid], j1 = (int)cl[(j + 1) * kBlock + tid];
-                        if (j0 >= (int)p.n || j1 >= (int)p.n) { confirm(j0); confirm(j1); continue; }   // padding record in the pair
-                        const double4 g0 = geo[j0], g1 = geo[j1];
-                        bool h0, h1; double r0 = 0.0, r1 = 0.0;
-                        sphere_root2(mk(g0.x, g0.y, g0.z), g0.w, mk(g1.x, g1.y, g1.z), g1.w, o, d, a, 0.001, h0, r0, h1, r1);
-                        consider(j0, h0, r0); consider(j1, h1, r1);
-                        st_cand += 2;
-                    }
-                }
-                for (; j < cnt; ++j) confirm((int)cl[j * kBlock + tid]);
-            };
-            const bool warp_has_ray = __ballot_sync(FULL, alive) != 0u;   // a warp whose 32 slots are all empty skips the scan (frame tail)
-            if (!EXACT && warp_has_ray) {
-                // per-ray filter constants in the recentred f32 frame (DESIGN.md "filter soundness")
-                float ofx = __double2float_rn(__dsub_rn(o.x, p.gx)), ofy = __double2float_rn(__dsub_rn(o.y, p.gy)),
-                      ofz = __double2float_rn(__dsub_rn(o.z, p.gz));
-                float dfx = __double2float_rn(d.x), dfy = __double2float_rn(d.y), dfz = __double2float_rn(d.z);
-                float s = fmaf(dfx, dfx, fmaf(dfy, dfy, dfz * dfz));
-                float oo = fmaf(ofx, ofx, fmaf(ofy, ofy, ofz * ofz));
-                bool ok = (s > 1e-30f) && (s < 1e30f) && (oo < 1e30f);
-                float inv = rsqrtf(s);
-                float dnx = dfx * inv, dny = dfy * inv, dnz = dfz * inv;
-                float nod = -fmaf(ofx, dnx, fmaf(ofy, dny, ofz * dnz));
-                float thr = __fmul_rd(oo, p.er_coef);
-                if (!alive) thr = __int_as_float(0x7fc00000);   // NaN: every comparison is false, so empty slots (whose o,d are garbage, possibly +-inf) never produce candidates
-                if (alive && !ok) { ovf = true; thr = __int_as_float(0x7fc00000); }
-                const float2 dx2 = make_float2(dnx, dnx), dy2 = make_float2(dny, dny), dz2 = make_float2(dnz, dnz);
-                const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy),
-                             oz2 = make_float2(2.f * ofz, 2.f * ofz);
-                const float2 nod2 = make_float2(nod, nod);
-                const uint32_t np = p.n_pairs;   // multiple of 8; padding records never hit
-                // Per-thread candidate lists live in shared memory as columns (entry k of thread t at [k*kBlock + t]); appends are
-                // predicated stores through a 32-bit shared address. A list that is about to fill up is drained on the spot, so
-                // no ray ever falls back to brute force because of list capacity.
-                const uint32_t l1_base = smem_u32(s_l1 + tid);
-                const uint32_t l1_full = l1_base + (uint32_t)(kWfMaxClus - 8) * kBlock * 2u;
-                uint32_t l1_addr = l1_base;
-                const uint32_t l2_base = smem_u32(s_l2 + tid);
-                const uint32_t l2_full = l2_base + (uint32_t)(kWfMaxCand - kClusterK) * kBlock * 2u;
-                uint32_t l2_addr = l2_base;
-#define RT_FILTER_PAIRS(REC, DV, NP)                                                                                                  \
-    _Pragma("unroll") for (int q = 0; q < (NP); ++q) {                                                                              \
-        float4 A = (REC)[2 * q], B = (REC)[2 * q + 1];                                                                               \
-        float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w), cz = make_float2(B.x, B.y), nk = make_float2(B.z, B.w);       \
-        float2 bb = __ffma2_rn(cz, dz2, nod2);                                                                                       \
-        float2 tt = __ffma2_rn(cz, oz2, nk);                                                                                         \
-        bb = __ffma2_rn(cy, dy2, bb);                                                                                                \
-        tt = __ffma2_rn(cy, oy2, tt);                                                                                                \
-        bb = __ffma2_rn(cx, dx2, bb);                                                                                                \
-        tt = __ffma2_rn(cx, ox2, tt);                                                                                                \
-        (DV)[q] = __ffma2_rn(bb, bb, tt);                                                                                            \
-    }
-#define RT_APPEND_IF(ADDR, VAL, ID)                                                                                                   \
-    asm volatile("{\n.reg .pred p;\n.reg .b16 h;\nsetp.ge.f32 p, %1, %2;\ncvt.u16.u32 h, %3;\n@p st.shared.u16 [%0], h;\n@p add.u32 %0, %0, %4;\n}" \
-                 : "+r"(ADDR) : "f"(VAL), "f"(thr), "r"(ID), "n"(kBlock * 2) : "memory")
-                // Loop structure: each level fills its list until it is nearly full (or its input ends), the next level drains
-                // it, and the outer loop resumes. Every drain therefore exists exactly once in the code (small I-cache footprint)
-                // and no ray ever falls back to brute force because of list capacity.
-                uint32_t pp = 0;
-                for (;;) {
-                    // ---- level 1: records of `filt` (cluster bounds, or the spheres themselves without clustering) ----
-#pragma unroll 1
-                    for (; pp < np && l1_addr <= l1_full; pp += 4) {
-                        float2 Dv[4];
-                        const float4* rec = s_filt + 2 * pp;
-                        RT_FILTER_PAIRS(rec, Dv, 4)
-                        // Without clustering a block rarely holds a candidate, so one max-reduction + branch guards the appends; with
-                        // clustering some lane of the warp hits nearly every block of cluster bounds, so the guard is dropped.
-                        bool any_hit = true;
-                        if (!TWO || RT_L1_GUARD) {
-                            float m = fmaxf(fmaxf(fmaxf(Dv[0].x, Dv[0].y), fmaxf(Dv[1].x, Dv[1].y)), fmaxf(fmaxf(Dv[2].x, Dv[2].y), fmaxf(Dv[3].x, Dv[3].y)));
-                            any_hit = m >= thr;
+            s_btu[tid] = kNoHitBits;
+            s_bi[tid] = 0xffffffffu;
+            if (MODE != MODE_EXACT) {
+                // per-ray constants in the recentred f32 frame (DESIGN.md "filter soundness")
+                const float ofx = __double2float_rn(__dsub_rn(o.x, p.gx)), ofy = __double2float_rn(__dsub_rn(o.y, p.gy)),
+                            ofz = __double2float_rn(__dsub_rn(o.z, p.gz));
+                const float dfx = __double2float_rn(d.x), dfy = __double2float_rn(d.y), dfz = __double2float_rn(d.z);
+                const float s = fmaf(dfx, dfx, fmaf(dfy, dfy, dfz * dfz));
+                const float oo = fmaf(ofx, ofx, fmaf(ofy, ofy, ofz * ofz));
+                const bool ok = (s > 1e-30f) && (s < 1e30f) && (oo < 1e30f);
+                const float inv = rsqrtf(s);
+                const float dnx = dfx * inv, dny = dfy * inv, dnz = dfz * inv;
+                const float nod = -fmaf(ofx, dnx, fmaf(ofy, dny, ofz * dnz));
+                const float thr = __fmul_rd(oo, p.er_coef);
+                if (alive && !ok) ovf = true;
+                if (MODE == MODE_TREE) {
+                    // slab constants: 1/d^ with |d^| clamped away from zero (keeps every product finite), margin 32u|o| rounded up
+                    const float ax = fabsf(dnx) < 1e-20f ? copysignf(1e-20f, dnx) : dnx;
+                    const float ay = fabsf(dny) < 1e-20f ? copysignf(1e-20f, dny) : dny;
+                    const float az = fabsf(dnz) < 1e-20f ? copysignf(1e-20f, dnz) : dnz;
+                    const float mray = __fmul_ru(1.9073486328125e-6f, __fsqrt_ru(oo));
+                    s_cA[tid] = make_float4(ofx, ofy, ofz, mray);
+                    s_cB[tid] = make_float4(__frcp_rn(ax), __frcp_rn(ay), __frcp_rn(az), thr);
+                    s_cC[tid] = make_float4(dnx, dny, dnz, nod);
+                    // ---- warp-cooperative traversal ----
+                    const bool enter = alive && ok && p.n_nodes != 0u;
+                    const unsigned em = __ballot_sync(FULL, enter);
+                    uint32_t n_in = (uint32_t)__popc(em), n_lf = 0u, n_cd = 0u;
+                    if (enter) wl_in[__popc(em & lt_mask)] = (uint32_t)lane;   // (root node 0) << 5 | ray
+                    __syncwarp();
+                    uint32_t guard = 0;
+                    for (;;) {
+                        if (n_in != 0u && n_lf <= (uint32_t)(kCapLf - 64)) {
+                            // ---------------- node step: lane <-> one (ray, node) pair from the top of the stack ----------------
+                            const uint32_t m = n_in < 32u ? n_in : 32u;
+                            const bool act = (uint32_t)lane < m;
+                            const uint32_t e = act ? wl_in[n_in - 1u - (uint32_t)lane] : 0u;
+                            const uint32_t ray = e & 31u, node = e >> 5;
+                            uint32_t hit = 0u, leafbits = 0u;
+                            const float4* N = nodes + (size_t)node * kNodeVec;
+                            if (act) {
+                                const float4 A = s_cA[wbase + ray], B = s_cB[wbase + ray];
+                                // near/far plane of each axis by the sign of d^; planes shifted outwards by the per-ray margin
+                                const uint32_t sx = __float_as_uint(B.x) >> 31, sy = __float_as_uint(B.y) >> 31, sz = __float_as_uint(B.z) >> 31;
+                                const float mx = copysignf(A.w, B.x), my = copysignf(A.w, B.y), mz = copysignf(A.w, B.z);
+                                const float cnx = __fmul_rn(__fadd_rn(A.x, mx), -B.x), cfx = __fmul_rn(__fsub_rn(A.x, mx), -B.x);
+                                const float cny = __fmul_rn(__fadd_rn(A.y, my), -B.y), cfy = __fmul_rn(__fsub_rn(A.y, my), -B.y);
+                                const float cnz = __fmul_rn(__fadd_rn(A.z, mz), -B.z), cfz = __fmul_rn(__fsub_rn(A.z, mz), -B.z);
+                                const float2 ix2 = make_float2(B.x, B.x), iy2 = make_float2(B.y, B.y), iz2 = make_float2(B.z, B.z);
+                                const float2 cnx2 = make_float2(cnx, cnx), cny2 = make_float2(cny, cny), cnz2 = make_float2(cnz, cnz);
+                                const float2 cfx2 = make_float2(cfx, cfx), cfy2 = make_float2(cfy, cfy), cfz2 = make_float2(cfz, cfz);
+                                const float4* Nnx = N + (sx ? 6 : 0); const float4* Nfx = N + (sx ? 0 : 6);
+                                const float4* Nny = N + (sy ? 8 : 2); const float4* Nfy = N + (sy ? 2 : 8);
+                                const float4* Nnz = N + (sz ? 10 : 4); const float4* Nfz = N + (sz ? 4 : 10);
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const float4 NX = Nnx[h], NY = Nny[h], NZ = Nnz[h], FX = Nfx[h], FY = Nfy[h], FZ = Nfz[h];
+                                    const float2 tnx0 = __ffma2_rn(make_float2(NX.x, NX.y), ix2, cnx2), tnx1 = __ffma2_rn(make_float2(NX.z, NX.w), ix2, cnx2);
+                                    const float2 tny0 = __ffma2_rn(make_float2(NY.x, NY.y), iy2, cny2), tny1 = __ffma2_rn(make_float2(NY.z, NY.w), iy2, cny2);
+                                    const float2 tnz0 = __ffma2_rn(make_float2(NZ.x, NZ.y), iz2, cnz2), tnz1 = __ffma2_rn(make_float2(NZ.z, NZ.w), iz2, cnz2);
+                                    const float2 tfx0 = __ffma2_rn(make_float2(FX.x, FX.y), ix2, cfx2), tfx1 = __ffma2_rn(make_float2(FX.z, FX.w), ix2, cfx2);
+                                    const float2 tfy0 = __ffma2_rn(make_float2(FY.x, FY.y), iy2, cfy2), tfy1 = __ffma2_rn(make_float2(FY.z, FY.w), iy2, cfy2);
+                                    const float2 tfz0 = __ffma2_rn(make_float2(FZ.x, FZ.y), iz2, cfz2), tfz1 = __ffma2_rn(make_float2(FZ.z, FZ.w), iz2, cfz2);
+                                    // hit iff max(t_near, 0) <= t_far
+                                    hit |= (fmaxf(fmax3(tnx0.x, tny0.x, tnz0.x), 0.f) <= fmin3(tfx0.x, tfy0.x, tfz0.x) ? 1u : 0u) << (4 * h + 0);
+                                    hit |= (fmaxf(fmax3(tnx0.y, tny0.y, tnz0.y), 0.f) <= fmin3(tfx0.y, tfy0.y, tfz0.y) ? 1u : 0u) << (4 * h + 1);
+                                    hit |= (fmaxf(fmax3(tnx1.x, tny1.x, tnz1.x), 0.f) <= fmin3(tfx1.x, tfy1.x, tfz1.x) ? 1u : 0u) << (4 * h + 2);
+                                    hit |= (fmaxf(fmax3(tnx1.y, tny1.y, tnz1.y), 0.f) <= fmin3(tfx1.y, tfy1.y, tfz1.y) ? 1u : 0u) << (4 * h + 3);
+                                }
+                                const uint4 R0 = *reinterpret_cast<const uint4*>(N + 12), R1 = *reinterpret_cast<const uint4*>(N + 13);
+                                leafbits = (R0.x >> 31) | ((R0.y >> 31) << 1) | ((R0.z >> 31) << 2) | ((R0.w >> 31) << 3) |
+                                           ((R1.x >> 31) << 4) | ((R1.y >> 31) << 5) | ((R1.z >> 31) << 6) | ((R1.w >> 31) << 7);
+                            }
+                            const uint32_t packed = (uint32_t)__popc(hit & ~leafbits) | ((uint32_t)__popc(hit & leafbits) << 16);
+                            const uint32_t inc = warp_scan_incl(packed, lane);
+                            // commit the longest prefix of lanes (top of the stack first) whose pushes fit
+                            const uint32_t new_in = n_in - ((uint32_t)lane + 1u) + (inc & 0xffffu);
+                            const bool fits = new_in <= (lane == 0 ? (uint32_t)kCapIn : fat_in) && n_lf + (inc >> 16) <= (uint32_t)kCapLf;
+                            const unsigned okm = __ballot_sync(FULL, fits || !act);
+                            uint32_t k = okm == FULL ? 32u : (uint32_t)(__ffs(~okm) - 1);
+                            k = k < m ? k : m;
+                            if (k == 0u) { if (lane == 0) atomicAdd(&p.err[1], 1ull); break; }   // cannot happen (reserve argument); never spin
+                            const uint32_t tot = __shfl_sync(FULL, inc, (int)k - 1);
+                            __syncwarp();   // every lane has read its entry before the stack is overwritten
+                            if (act && (uint32_t)lane < k) {
+                                const uint32_t exc = inc - packed;
+                                uint32_t pi = (n_in - k) + (exc & 0xffffu), pl = n_lf + (exc >> 16);
+                                const uint32_t* refs = reinterpret_cast<const uint32_t*>(N + 12);
+                                uint32_t mm = hit;
+                                while (mm) {
+                                    const int c = __ffs(mm) - 1;
+                                    mm &= mm - 1u;
+                                    const uint32_t ref = refs[c];
+                                    if (ref & kLeafBit) wl_lf[pl++] = (ref << 5) | ray;   // the shift drops the leaf bit
+                                    else wl_in[pi++] = (ref << 5) | ray;
+                                }
+                                ++st_nodes;
+                            }
+                            n_in = n_in - k + (tot & 0xffffu);
+                            n_lf += tot >> 16;
+                            __syncwarp();
+                        } else if (n_lf != 0u && n_cd <= (uint32_t)(kCapCd - 64)) {
+                            // ---------------- leaf step: lane <-> one (ray, leaf) pair: conservative sphere test on its spheres ----------------
+                            const uint32_t m = n_lf < 32u ? n_lf : 32u;
+                            const bool act = (uint32_t)lane < m;
+                            const uint32_t e = act ? wl_lf[n_lf - 1u - (uint32_t)lane] : 0u;
+                            const uint32_t ray = e & 31u, leaf = e >> 5;
+                            uint32_t hit = 0u;
+                            if (act) {
+                                const float4 A = s_cA[wbase + ray], C = s_cC[wbase + ray];
+                                const float th = s_cB[wbase + ray].w;
+                                const float2 dx2 = make_float2(C.x, C.x), dy2 = make_float2(C.y, C.y), dz2 = make_float2(C.z, C.z);
+                                const float2 ox2 = make_float2(2.f * A.x, 2.f * A.x), oy2 = make_float2(2.f * A.y, 2.f * A.y), oz2 = make_float2(2.f * A.z, 2.f * A.z);
+                                const float2 nod2 = make_float2(C.w, C.w);
+                                float2 Dv[kLeafK / 2];
+                                const float4* rec = leaf_rec + (size_t)leaf * kLeafK;
+                                RT_FILTER_PAIRS(rec, Dv, kLeafK / 2)
+#pragma unroll
+                                for (int q = 0; q < kLeafK / 2; ++q) hit |= (Dv[q].x >= th ? 1u : 0u) << (2 * q) | (Dv[q].y >= th ? 1u : 0u) << (2 * q + 1);
+                            }
+                            const uint32_t cntc = (uint32_t)__popc(hit);
+                            const uint32_t inc = warp_scan_incl(cntc, lane);
+                            const bool fits = n_cd + inc <= (uint32_t)kCapCd;
+                            const unsigned okm = __ballot_sync(FULL, fits || !act);
+                            uint32_t k = okm == FULL ? 32u : (uint32_t)(__ffs(~okm) - 1);
+                            k = k < m ? k : m;
+                            if (k == 0u) { if (lane == 0) atomicAdd(&p.err[1], 1ull); break; }
+                            const uint32_t tot = __shfl_sync(FULL, inc, (int)k - 1);
+                            if (act && (uint32_t)lane < k) {
+                                uint32_t pc = n_cd + inc - cntc;
+                                const uint32_t* ids = leaf_id + (size_t)leaf * kLeafK;
+                                uint32_t mm = hit;
+                                while (mm) {
+                                    const int c = __ffs(mm) - 1;
+                                    mm &= mm - 1u;
+                                    wl_cd[pc++] = (ids[c] << 5) | ray;
+                                }
+                                ++st_leaves;
+                            }
+                            n_lf -= k;
+                            n_cd += tot;
+                            __syncwarp();
+                        } else if (n_cd != 0u) {
+                            // ---------------- exact step: lane <-> one (ray, sphere) candidate, reference-exact f64 Sphere::hit ----------------
+                            const uint32_t m = n_cd < 32u ? n_cd : 32u;
+                            const bool act = (uint32_t)lane < m;
+                            const uint32_t e = act ? wl_cd[n_cd - 1u - (uint32_t)lane] : 0u;
+                            const uint32_t slot = wbase + (e & 31u), sph = e >> 5;
+                            unsigned long long key = ~0ull;
+                            if (act) {
+                                const D3 ro = mk(s_ox[slot], s_oy[slot], s_oz[slot]), rd = mk(s_dx[slot], s_dy[slot], s_dz[slot]);
+                                const double4 gq = geo[sph];
+                                double root;
+                                if (sphere_root(mk(gq.x, gq.y, gq.z), gq.w, ro, rd, length_squared(rd), 0.001, DBL_MAX, root)) key = (unsigned long long)__double_as_longlong(root);
+                                ++st_cand;
+                            }
+                            // per-ray lexicographic minimum of (root, sphere index): roots are positive, so their bit patterns order like the values
+                            const bool h = key != ~0ull;
+                            const unsigned long long before = h ? s_btu[slot] : 0ull;
+                            __syncwarp();
+                            if (h && key < before) atomicMin(&s_btu[slot], key);
+                            __syncwarp();
+                            const bool mine = h && key == s_btu[slot];
+                            if (mine && key < before) atomicMax(&s_bi[slot], 0xffffffffu);   // the root got smaller in this step: forget the old index
+                            __syncwarp();
+                            if (mine) atomicMin(&s_bi[slot], sph);
+                            n_cd -= m;
+                            __syncwarp();
+                        } else {
+                            break;
                         }
-                        if (any_hit) {
-                            const uint32_t j0 = 2u * pp;
+                        if (++guard > (1u << 22)) { if (lane == 0) atomicAdd(&p.err[1], 1ull); break; }
+                    }
+                    PF_MARK(pf_trav)
+                } else {   // MODE_BRUTE: hit_world's linear scan with the conservative sphere test in front of the exact one
+                    if (alive && ok) {
+                        const float2 dx2 = make_float2(dnx, dnx), dy2 = make_float2(dny, dny), dz2 = make_float2(dnz, dnz);
+                        const float2 ox2 = make_float2(2.f * ofx, 2.f * ofx), oy2 = make_float2(2.f * ofy, 2.f * ofy), oz2 = make_float2(2.f * ofz, 2.f * ofz);
+                        const float2 nod2 = make_float2(nod, nod);
+#pragma unroll 1
+                        for (uint32_t pp = 0; pp < p.n_pairs; pp += 4) {
+                            float2 Dv[4];
+                            const float4* rec = s_filt + 2 * pp;
+                            RT_FILTER_PAIRS(rec, Dv, 4)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                RT_APPEND_IF(l1_addr, Dv[q].x, j0 + 2u * q);
-                                RT_APPEND_IF(l1_addr, Dv[q].y, j0 + 2u * q + 1u);
+                                const uint32_t j = 2u * (pp + (uint32_t)q);
+                                if (Dv[q].x >= thr && j < p.n) confirm((int)j);
+                                if (Dv[q].y >= thr && j + 1u < p.n) confirm((int)j + 1);
                             }
                         }
                     }
-                    if (TWO) {
-                        // ---- level 2: the kClusterK member spheres of every listed cluster (per-thread addresses) ----
-                        const int n1 = (int)((l1_addr - l1_base) / (kBlock * 2u));
-                        const float beta_o = 16.0f * 5.9604645e-8f * sqrtf(oo);      // rounding bound of b = (c-o).d on the ray's side
-                        int k = 0;
-                        for (;;) {
-#pragma unroll 1
-                            for (; k < n1 && l2_addr <= l2_full; ++k) {
-                                const uint32_t cb = s_l1[k * kBlock + tid];
-                                if (cb >= p.n_clusters) continue;                   // padding record
-                                // Behind-the-origin cull: with b = (c-o).d^ and q = |c-o|^2 - R^2, b < 0 and q > 0 put both roots of
-                                // the bounding sphere at negative t, hence every member root too. Both signs are required beyond
-                                // their rounding margins, otherwise the cluster is processed.
-                                const uint32_t pr = cb >> 1, hi = cb & 1u;
-                                const float4 CA = s_filt[2 * pr], CB = s_filt[2 * pr + 1];
-                                const float ccx = hi ? CA.y : CA.x, ccy = hi ? CA.w : CA.z, ccz = hi ? CB.y : CB.x, cnk = hi ? CB.w : CB.z;
-                                const float cbb = fmaf(ccx, dnx, fmaf(ccy, dny, fmaf(ccz, dnz, nod)));
-                                const float ctt = fmaf(ccx, 2.f * ofx, fmaf(ccy, 2.f * ofy, fmaf(ccz, 2.f * ofz, cnk)));
-                                const float cD = fmaf(cbb, cbb, ctt);               // ~ b^2 - q + Es + |o|^2
-                                const float cabs = cmeta[cb];                       // |c| of the bound (f32, rounded up)
-                                const float qlow = fmaf(cbb, cbb, oo) - cD;         // ~ q - Es  (<= q up to rounding)
-                                const float eq = 2.0e-5f * fmaf(cabs, cabs, oo);    // >= 3x the rounding bound 96u(|c|^2+|o|^2)
-                                if (cbb < -(16.0f * 5.9604645e-8f * cabs + beta_o) * 1.5f - 1e-30f && qlow > eq) continue;
-                                float2 Dv[kClusterK / 2];
-                                const float4* rec = sfilt + (uint32_t)kClusterK * cb;
-                                RT_FILTER_PAIRS(rec, Dv, kClusterK / 2)
-                                float m = fmaxf(Dv[0].x, Dv[0].y);
-#pragma unroll
-                                for (int q = 1; q < kClusterK / 2; ++q) m = fmaxf(m, fmaxf(Dv[q].x, Dv[q].y));
-                                if (m >= thr) {
-                                    const uint16_t* og = orig + (uint32_t)kClusterK * cb;
-#pragma unroll
-                                    for (int q = 0; q < kClusterK / 2; ++q) {
-                                        const uint32_t w = *reinterpret_cast<const uint32_t*>(og + 2 * q);   // 2 x u16 slot -> sphere index
-                                        RT_APPEND_IF(l2_addr, Dv[q].x, w & 0xffffu);
-                                        RT_APPEND_IF(l2_addr, Dv[q].y, w >> 16);
-                                    }
-                                }
-                                ++st_clus;
-                            }
-                            // ---- exact f64 confirmation of the listed spheres ----
-                            const int n2 = (int)((l2_addr - l2_base) / (kBlock * 2u));
-                            confirm_list(s_l2, n2);
-                            l2_addr = l2_base;
-                            if (k >= n1) break;
-                        }
-                        l1_addr = l1_base;
-                    } else {
-                        const int n1 = (int)((l1_addr - l1_base) / (kBlock * 2u));
-                        confirm_list(s_l1, n1);
-                        l1_addr = l1_base;
-                    }
-                    if (pp >= np) break;
                 }
-                PF_MARK(pf_scan)
-#undef RT_FILTER_PAIRS
-#undef RT_APPEND_IF
-            } else if (EXACT) {
+            } else {
                 ovf = alive;
             }
             if (alive) {
-                if (ovf) {   // EXACT variant, or a ray outside the f32 filter's safe range: every sphere in f64
+                if (ovf) {   // MODE_EXACT, or a ray outside the f32 frame's safe range: every sphere in f64
                     ++st_ovf;
                     for (int k = 0; k < (int)p.n; ++k) confirm(k);
+                } else if (MODE == MODE_TREE) {
+                    for (uint32_t k = 0; k < p.n_always; ++k) confirm((int)p.always[k]);
                 }
-                s_bt[tid] = best_t;
-                s_bi[tid] = (uint32_t)best;
-                cls = CLS_MISS;
+                // merge the thread-private result with the traversal's (this slot is only touched by its own thread now)
+                const unsigned long long tb = s_btu[tid];
+                const uint32_t ti = s_bi[tid];
                 if (best >= 0) {
-                    uint32_t kind = mat[best].kind;
+                    const unsigned long long kb = (unsigned long long)__double_as_longlong(best_t);
+                    if (ti == 0xffffffffu || kb < tb || (kb == tb && (uint32_t)best < ti)) { s_bt[tid] = best_t; s_bi[tid] = (uint32_t)best; }
+                }
+                const uint32_t fin = s_bi[tid];
+                cls = CLS_MISS;
+                if (fin != 0xffffffffu) {
+                    uint32_t kind = mat[fin].kind;
                     cls = (kind == RT_METAL) ? CLS_METAL : (kind == RT_GLASS) ? CLS_GLASS : (kind == RT_LIGHT) ? CLS_LIGHT : CLS_DIFFUSE;
                 }
                 ++st_rays;
             }
         }
-        PF_MARK(pf_confirm)
+        PF_MARK(pf_exact)
 
         // =========================== sort: compact the live slots class by class ===========================
-        uint32_t wbase = 0, rank = 0;
+        uint32_t wbase_c = 0, rank = 0;
 #pragma unroll
         for (uint32_t c = 0; c < CLS_DEAD; ++c) {
             unsigned b = __ballot_sync(FULL, cls == c);
@@ -422,17 +511,17 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(b));
                 base = __shfl_sync(FULL, base, 0);
-                if (cls == c) { wbase = base; rank = __popc(b & ((1u << lane) - 1u)); }
+                if (cls == c) { wbase_c = base; rank = __popc(b & lt_mask); }
             }
         }
         PF_MARK(pf_sort)
-        __syncthreads();   // A: class counts complete
+        __syncthreads();   // A: class counts complete (and every warp's closest-hit results are in the pool)
         PF_MARK(pf_waitA)
         uint32_t c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3], c4 = cnt[4];
         const uint32_t e0 = c0, e1 = e0 + c1, e2 = e1 + c2, e3 = e2 + c3, n_live = e3 + c4;   // class end offsets
         if (cls != CLS_DEAD) {
             uint32_t start = cls == 0 ? 0u : cls == 1 ? e0 : cls == 2 ? e1 : cls == 3 ? e2 : e3;
-            s_perm[start + wbase + rank] = (uint16_t)tid;
+            s_perm[start + wbase_c + rank] = (uint16_t)tid;
         }
         if (tid < 8) s_cnt[((it + 1u) & 1u) * 8u + tid] = 0u;   // reset the other counter set for the next iteration
         __syncthreads();   // B: perm complete
@@ -511,7 +600,7 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
                             const unsigned long long depth_now = (unsigned long long)p.max_depth - level;
                             const bool depth_ok = (shd > 0u) ? true : (depth_now > (unsigned long long)p.max_depth - 2ull);   // usize wrap like a release build
                             pass = (xi > __dsub_rn(1.0, __dmul_rn((double)p.n_lights, prob))) && depth_ok;
-                            if (pass && shd >= p.max_shadow) { pass = false; atomicAdd(&p.stat[5], 1ull); }   // reported as an error by the host
+                            if (pass && shd >= p.max_shadow) { pass = false; atomicAdd(&p.err[0], 1ull); }   // reported as an error by the host
                         }
                         if (pass) {
                             float ar, ag, ab;
@@ -614,7 +703,7 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
 
 #ifdef RT_PROFILE_PHASES
     if (lane == 0) {   // per-warp cycle totals of each phase
-        atomicAdd(&p.stat[8], pf_scan); atomicAdd(&p.stat[9], pf_confirm); atomicAdd(&p.stat[10], pf_waitA); atomicAdd(&p.stat[11], pf_sort);
+        atomicAdd(&p.stat[8], pf_trav); atomicAdd(&p.stat[9], pf_exact); atomicAdd(&p.stat[10], pf_waitA); atomicAdd(&p.stat[11], pf_sort);
         atomicAdd(&p.stat[12], pf_shade); atomicAdd(&p.stat[13], pf_waitC); atomicAdd(&p.stat[14], pf_iters);
     }
 #endif
@@ -625,53 +714,66 @@ __global__ void __launch_bounds__(kBlock, MINB) rt_wavefront_kernel(const __grid
         st_cand += __shfl_down_sync(FULL, st_cand, off);
         st_ovf += __shfl_down_sync(FULL, st_ovf, off);
         st_samples += __shfl_down_sync(FULL, st_samples, off);
-        st_clus += __shfl_down_sync(FULL, st_clus, off);
+        st_leaves += __shfl_down_sync(FULL, st_leaves, off);
+        st_nodes += __shfl_down_sync(FULL, st_nodes, off);
     }
     if (lane == 0) {
-        atomicAdd(&p.stat[4], st_clus);
         atomicAdd(&p.stat[0], st_rays);
         atomicAdd(&p.stat[1], st_cand);
         atomicAdd(&p.stat[2], st_ovf);
         atomicAdd(&p.stat[3], st_samples);
+        atomicAdd(&p.stat[4], st_leaves);
+        atomicAdd(&p.stat[6], st_nodes);
     }
 }
 
-// MINB = CTAs per SM the register allocation targets: 4 (64 registers, small spills) when shared memory lets four pools be
-// resident, else 2 (up to 128 registers, no spills) - e.g. when 10 k spheres' first-level records take 40 KB per CTA.
-template <int MB, bool E, bool LI, bool TW>
+// MINB = CTAs per SM the register allocation targets (3: up to 80 registers; 2: up to 128 when shared memory only lets
+// two pools be resident).
+template <int MB, uint32_t MODE, bool LI>
 static cudaError_t launch_wf(const TraceParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<256, MB, E, LI, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rt_wavefront_kernel<MB, MODE, LI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rt_wavefront_kernel<256, MB, E, LI, TW><<<grid, 256, smem, st>>>(p);
+    rt_wavefront_kernel<MB, MODE, LI><<<grid, kBlock, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int MB>
-static cudaError_t launch_wf_minb(const TraceParams& p, int grid, size_t smem, bool exact, cudaStream_t st) {
-    const bool li = p.n_lights > 0, tw = p.two_level != 0;
-    if (exact) {   // every sphere in f64: the filter levels are not used at all
-        return li ? launch_wf<MB, true, true, false>(p, grid, smem, st) : launch_wf<MB, true, false, false>(p, grid, smem, st);
-    }
-    if (tw) return li ? launch_wf<MB, false, true, true>(p, grid, smem, st) : launch_wf<MB, false, false, true>(p, grid, smem, st);
-    return li ? launch_wf<MB, false, true, false>(p, grid, smem, st) : launch_wf<MB, false, false, false>(p, grid, smem, st);
+template <typename F>
+static auto dispatch(uint32_t mode, bool lights, int minb, F&& f) {
+    // the validation modes exist in one register budget only
+    if (mode == MODE_EXACT) return lights ? f(rt_wavefront_kernel<2, MODE_EXACT, true>) : f(rt_wavefront_kernel<2, MODE_EXACT, false>);
+    if (mode == MODE_BRUTE) return lights ? f(rt_wavefront_kernel<2, MODE_BRUTE, true>) : f(rt_wavefront_kernel<2, MODE_BRUTE, false>);
+    if (minb >= 3) return lights ? f(rt_wavefront_kernel<3, MODE_TREE, true>) : f(rt_wavefront_kernel<3, MODE_TREE, false>);
+    return lights ? f(rt_wavefront_kernel<2, MODE_TREE, true>) : f(rt_wavefront_kernel<2, MODE_TREE, false>);
 }
 
-cudaError_t launch_wavefront(const TraceParams& p, int grid, size_t smem, int minb, bool exact, cudaStream_t st) {
-    return minb >= 4 ? launch_wf_minb<4>(p, grid, smem, exact, st) : launch_wf_minb<2>(p, grid, smem, exact, st);
+cudaError_t launch_wavefront(const TraceParams& p, uint32_t mode, int grid, size_t smem, int minb, cudaStream_t st) {
+    return dispatch(mode, p.n_lights > 0, minb, [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kBlock, smem, st>>>(p);
+        return cudaGetLastError();
+    });
 }
 
-int wavefront_max_ctas_per_sm(size_t smem, int minb) {
-    int nb = 0;
-    cudaError_t e;
-    if (minb >= 4) {
-        cudaFuncSetAttribute(rt_wavefront_kernel<256, 4, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, 4, false, true, true>, 256, smem);
-    } else {
-        cudaFuncSetAttribute(rt_wavefront_kernel<256, 2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rt_wavefront_kernel<256, 2, false, true, true>, 256, smem);
-    }
-    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
-    return nb;
+int wavefront_max_ctas_per_sm(uint32_t mode, bool lights, size_t smem, int minb) {
+    return dispatch(mode, lights, minb, [&](auto kern) -> int {
+        int nb = 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kBlock, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return nb;
+    });
+}
+
+cudaError_t wavefront_info(uint32_t mode, bool lights, int minb, KernelInfo* out) {
+    return dispatch(mode, lights, minb, [&](auto kern) -> cudaError_t {
+        cudaFuncAttributes a;
+        cudaError_t e = cudaFuncGetAttributes(&a, kern);
+        if (e != cudaSuccess) return e;
+        out->registers = a.numRegs; out->max_threads = a.maxThreadsPerBlock; out->const_bytes = (int)a.constSizeBytes; out->local_bytes = (int)a.localSizeBytes;
+        snprintf(out->name, sizeof out->name, "rt_wavefront_kernel<%d,%s,%s>", mode == MODE_TREE ? (minb >= 3 ? 3 : 2) : 2,
+                 mode == MODE_TREE ? "MODE_TREE" : mode == MODE_BRUTE ? "MODE_BRUTE" : "MODE_EXACT", lights ? "LIGHTS" : "NO_LIGHTS");
+        return cudaSuccess;
+    });
 }
 
 }  // namespace rtk

@@ -119,14 +119,16 @@ bool decode_jpeg(const uint8_t* data, size_t size, Image* out, std::string* err)
         if (m == 0xFF) { ++i; continue; }
         if (m == 0xD9) break;
         size_t L = ((size_t)data[i + 2] << 8) | data[i + 3];
+        if (L < 2) return fail("segment length below 2");
         if (i + 2 + L > size) return fail("truncated segment");
         const uint8_t* s = data + i + 4;
-        size_t n = L - 2;
+        size_t n = L - 2;                                  // payload bytes: every read below is checked against it
         if (m == 0xDB) {                                   // DQT
             size_t k = 0;
             while (k < n) {
                 int pq = s[k] >> 4, tq = s[k] & 15; ++k;
-                if (tq > 3) return fail("bad DQT id");
+                if (tq > 3 || pq > 1) return fail("bad DQT id / precision");
+                if (k + (size_t)64 * (pq ? 2 : 1) > n) return fail("truncated DQT");
                 for (int j = 0; j < 64; ++j) {
                     uint16_t v = pq ? (uint16_t)((s[k] << 8) | s[k + 1]) : s[k];
                     k += pq ? 2 : 1;
@@ -140,31 +142,45 @@ bool decode_jpeg(const uint8_t* data, size_t size, Image* out, std::string* err)
                 if (th > 3 || tc > 1) return fail("bad DHT id");
                 Huff& h = tc ? hac[th] : hdc[th];
                 int total = 0;
+                if (k + 16 > n) return fail("truncated DHT");
                 for (int l = 1; l <= 16; ++l) { h.bits[l] = s[k++]; total += h.bits[l]; }
                 if (total > 256) return fail("bad DHT");
+                if (k + (size_t)total > n) return fail("truncated DHT");
                 for (int j = 0; j < total; ++j) h.vals[j] = s[k++];
                 h.build();
             }
         } else if (m == 0xC0 || m == 0xC1) {               // SOF0 / SOF1
+            if (n < 6) return fail("truncated SOF");
             if (s[0] != 8) return fail("only 8-bit JPEG is supported");
             height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4]; ncomp = s[5];
+            if (width == 0 || height == 0) return fail("zero image dimension");
             if (ncomp != 1 && ncomp != 3) return fail("only 1 or 3 components are supported");
-            for (int c = 0; c < ncomp; ++c) { comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c]; }
+            if (n < (size_t)(6 + 3 * ncomp)) return fail("truncated SOF");
+            for (int c = 0; c < ncomp; ++c) {
+                comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c];
+                if (comps[c].tq > 3) return fail("bad quantisation table id");
+                comps[c].td = 0; comps[c].ta = 0;
+            }
             got_sof = true;
         } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
             return fail("progressive / arithmetic / lossless JPEG is not supported");
         } else if (m == 0xDD) {
+            if (n < 2) return fail("truncated DRI");
             restart = (s[0] << 8) | s[1];
         } else if (m == 0xEE && n >= 12 && std::memcmp(s, "Adobe", 5) == 0) {
             adobe_transform = s[11];
         } else if (m == 0xDA) {                            // SOS: the entropy-coded data follows
             if (!got_sof) return fail("SOS before SOF");
+            if (n < 1) return fail("truncated SOS");
             int ns = s[0];
             if (ns != ncomp) return fail("non-interleaved scans are not supported");
+            if (n < (size_t)(1 + 2 * ns)) return fail("truncated SOS");
             for (int k = 0; k < ns; ++k) {
                 int cid = s[1 + 2 * k];
+                const int td = s[2 + 2 * k] >> 4, ta = s[2 + 2 * k] & 15;
+                if (td > 3 || ta > 3) return fail("bad Huffman table id");
                 for (int c = 0; c < ncomp; ++c)
-                    if (comps[c].id == cid) { comps[c].td = s[2 + 2 * k] >> 4; comps[c].ta = s[2 + 2 * k] & 15; }
+                    if (comps[c].id == cid) { comps[c].td = td; comps[c].ta = ta; }
             }
             i += 2 + L;
             int hmax = 1, vmax = 1;

@@ -1,7 +1,8 @@
 // raytracer <config_file> <output_file> — the reference CLI (main.rs:7-20) on top of librtb200.so.
 // Same argument contract, same two stdout lines ("\nRendering <file>", "Frame time: <ms>ms"); errors that make the
 // reference panic print a message to stderr and exit with status 101 (Rust's panic exit code).
-// Extra knobs, so the CLI stays identical: RTB200_SEED, RTB200_DEVICE, RTB200_STATS=1 (prints rays / Mrays/s to stderr).
+// Extra knobs, so the CLI stays identical: RTB200_SEED, RTB200_DEVICE, RTB200_GPUS=<n|0=all> (row bands dealt over n GPUs of
+// this process, rtb200_render_rgb8_multi), RTB200_STATS=1 (prints rays / Mrays/s to stderr).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -37,13 +38,15 @@ int main(int argc, char** argv) {
     opts.device = getenv("RTB200_DEVICE") ? atoi(getenv("RTB200_DEVICE")) : -1; opts.rank = 0; opts.world = 1; opts.band_rows = 1;
     rt_stats st{};
     auto t0 = std::chrono::steady_clock::now();                           // raytracer.rs:259
-    int rc = rtb200_render_rgb8(&s, &opts, pixels.data(), &st);           // replaces raytracer.rs:260-262
+    const char* gpus = getenv("RTB200_GPUS");
+    int rc = gpus ? rtb200_render_rgb8_multi(&s, &opts, atoi(gpus), pixels.data(), &st)   // replaces raytracer.rs:260-262
+                  : rtb200_render_rgb8(&s, &opts, pixels.data(), &st);
     if (rc != 0) { fprintf(stderr, "render failed (%d): %s\n", rc, rtb200_last_error()); return 101; }
     long long ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
     printf("Frame time: %lldms\n", ms);                                   // raytracer.rs:263
     if (getenv("RTB200_STATS"))
-        fprintf(stderr, "rays=%llu samples=%llu device_ms=%.3f Mrays/s=%.1f\n", (unsigned long long)st.rays, (unsigned long long)st.samples, st.device_ms,
-                st.device_ms > 0 ? st.rays / st.device_ms / 1e3 : 0.0);
+        fprintf(stderr, "rays=%llu samples=%llu device_ms=%.3f Mrays/s=%.1f gpus=%d\n", (unsigned long long)st.rays, (unsigned long long)st.samples, st.device_ms,
+                st.device_ms > 0 ? st.rays / st.device_ms / 1e3 : 0.0, (int)st.gpus_used);
     std::string err;
     if (!rthost::write_png_rgb8(argv[2], pixels.data(), s.width, s.height, &err)) { fprintf(stderr, "error writing image: %s\n", err.c_str()); return 101; }   // raytracer.rs:265
     return 0;

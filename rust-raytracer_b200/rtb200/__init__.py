@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(os.path.dirname(_HERE), 
 
 RT_LAMBERTIAN, RT_METAL, RT_GLASS, RT_TEXTURE, RT_LIGHT = 0, 1, 2, 3, 4
 RT_SKY_NONE, RT_SKY_GRADIENT, RT_SKY_TEXTURE = 0, 1, 2
-RT_VARIANT_AUTO, RT_VARIANT_FILTERED, RT_VARIANT_EXACT_F64, RT_VARIANT_LANES, RT_VARIANT_BRUTE_FORCE = 0, 1, 2, 3, 4
+RT_VARIANT_AUTO, RT_VARIANT_FILTERED, RT_VARIANT_EXACT_F64, RT_VARIANT_RETIRED_LANES, RT_VARIANT_BRUTE_FORCE = 0, 1, 2, 3, 4
 
 DEFAULT_SEED = 0x5EED
 
@@ -54,7 +54,7 @@ class rt_sphere(C.Structure):
 
 
 class rt_image(C.Structure):
-    _fields_ = [("rgb8", C.c_void_p), ("width", C.c_uint64), ("height", C.c_uint64)]
+    _fields_ = [("rgb8", C.c_void_p), ("width", C.c_uint64), ("height", C.c_uint64), ("bytes", C.c_uint64)]
 
 
 class rt_sky(C.Structure):
@@ -78,10 +78,22 @@ class rt_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("candidates", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("wall_ms", C.c_double),
                 ("kernel_launches", C.c_uint32), ("batches", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("clusters", C.c_uint64), ("frames", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("clusters", C.c_uint64), ("frames", C.c_uint64),
+                ("nodes", C.c_uint64), ("gpus_used", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class rt_kernel_info(C.Structure):
+    _fields_ = [("registers", C.c_int32), ("local_bytes", C.c_int32), ("smem_bytes", C.c_uint32), ("grid", C.c_uint32),
+                ("block", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("smem_mask", C.c_uint32), ("bvh_nodes", C.c_uint32),
+                ("bvh_leaves", C.c_uint32), ("bvh_depth", C.c_uint32), ("name", C.c_char * 96)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["name"] = d["name"].decode()
+        return d
 
 
 assert C.sizeof(rt_sphere) == 64
@@ -93,7 +105,7 @@ ABI_SYMBOLS = [
     "rtb200_scene_release", "rtb200_probe_sphere_hit", "rtb200_probe_refract", "rtb200_probe_reflectance",
     "rtb200_probe_sky", "rtb200_probe_get_ray", "rtb200_probe_rng", "rtb200_probe_quantise",
     "rtb200_decode_jpeg_file", "rtb200_free", "rtb200_render_device_async", "rtb200_render_device_wait",
-    "rtb200_debug_filter_records", "rtb200_probe_sphere_uv",
+    "rtb200_debug_bvh", "rtb200_probe_sphere_uv", "rtb200_device_count", "rtb200_render_rgb8_multi", "rtb200_scene_kernel_info",
 ]
 
 _lib = None
@@ -131,8 +143,12 @@ def lib() -> C.CDLL:
     L.rtb200_decode_jpeg_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rtb200_free.argtypes = [C.c_void_p]
     L.rtb200_free.restype = None
-    L.rtb200_debug_filter_records.argtypes = [C.POINTER(rt_scene), C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64,
-                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.rtb200_debug_bvh.argtypes = [C.POINTER(rt_scene), C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64,
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.rtb200_probe_sphere_uv.argtypes = [C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_double)]
+    L.rtb200_device_count.restype = C.c_int
+    L.rtb200_render_rgb8_multi.argtypes = [C.POINTER(rt_scene), C.POINTER(rt_options), C.c_int32, C.c_void_p, C.POINTER(rt_stats)]
+    L.rtb200_scene_kernel_info.argtypes = [C.c_void_p, C.POINTER(rt_kernel_info)]
     _lib = L
     return L
 
@@ -232,7 +248,7 @@ class Scene:
                 arr = _decode_jpeg(os.path.join(base_dir, tex))
                 sc._sky_array = arr
                 sc.c.sky.mode = RT_SKY_TEXTURE
-                sc.c.sky.tex = rt_image(arr.ctypes.data, arr.shape[1], arr.shape[0])
+                sc.c.sky.tex = rt_image(arr.ctypes.data, arr.shape[1], arr.shape[0], arr.size)
         objs = cfg.get("objects", [])
         arr_t = rt_sphere * max(len(objs), 1)
         sc._spheres = arr_t()
@@ -256,7 +272,7 @@ class Scene:
                 if w * h * 3 > arr.size:
                     raise ValueError(f"texture {body['pixels']}: JSON says {w}x{h} but the file holds {arr.shape[1]}x{arr.shape[0]}")
                 sc._tex_arrays.append(arr)
-                tex_structs.append(rt_image(arr.ctypes.data, w, h))
+                tex_structs.append(rt_image(arr.ctypes.data, w, h, arr.size))
                 s.texture = len(tex_structs) - 1
             elif kind == "Light":
                 s.kind = RT_LIGHT
@@ -319,19 +335,21 @@ def load_scene(path: str, base_dir: Optional[str] = None) -> Scene:
     return Scene.from_config(cfg, base_dir)
 
 
-def filter_records(scene: "Scene", variant: int = RT_VARIANT_AUTO) -> dict:
-    """Host-side diagnostic: the conservative filter records of the closest-hit stage (no GPU needed)."""
+def bvh_records(scene: "Scene") -> dict:
+    """Host-side diagnostic: the hierarchy the closest-hit stage traverses (no GPU needed). See rtb200_debug_bvh."""
     n = scene.n_spheres
-    cap_c = 2 * n + 64
-    first = np.zeros(8 * (cap_c + 16), np.float32); second = np.zeros(4 * 8 * cap_c, np.float32)
-    slots = np.zeros(8 * cap_c, np.uint16); cabs = np.zeros(cap_c, np.float32)
-    g = (C.c_double * 3)(); info = (C.c_uint32 * 4)()
-    _check(lib().rtb200_debug_filter_records(C.byref(scene.c), variant, g, info, first.ctypes.data, first.size, second.ctypes.data, second.size,
-                                             slots.ctypes.data, slots.size, cabs.ctypes.data, cabs.size))
-    two, n_pairs, n_clusters, k = (int(x) for x in info)
-    return {"two_level": bool(two), "n_pairs": n_pairs, "n_clusters": n_clusters, "cluster_size": k, "recentre": np.array(g[:]),
-            "first": first[: n_pairs * 8].reshape(n_pairs, 2, 4), "second": second[: n_clusters * k * 4].reshape(n_clusters, k // 2, 2, 4),
-            "slot_to_sphere": slots[: n_clusters * k].reshape(n_clusters, k), "cluster_abs": cabs[:n_clusters]}
+    g = (C.c_double * 3)(); info = (C.c_uint32 * 8)()
+    _check(lib().rtb200_debug_bvh(C.byref(scene.c), g, info, None, 0, None, 0, None, 0, None, 0, None, 0))
+    n_nodes, n_leaves, depth, k, n_always, fpn, n_pairs, _ = (int(x) for x in info)
+    nodes = np.zeros(max(n_nodes * fpn, 1), np.float32); rec = np.zeros(max(n_leaves * k * 4, 1), np.float32)
+    ids = np.zeros(max(n_leaves * k, 1), np.uint32); always = np.zeros(max(n_always, 1), np.uint32); flat = np.zeros(max(n_pairs * 8, 1), np.float32)
+    _check(lib().rtb200_debug_bvh(C.byref(scene.c), g, info, nodes.ctypes.data, nodes.size, rec.ctypes.data, rec.size, ids.ctypes.data, ids.size,
+                                  always.ctypes.data, always.size, flat.ctypes.data, flat.size))
+    nd = nodes[: n_nodes * fpn].reshape(n_nodes, fpn)
+    return {"n_nodes": n_nodes, "n_leaves": n_leaves, "depth": depth, "leaf_size": k, "recentre": np.array(g[:]), "n": n,
+            "lo": nd[:, :24].reshape(n_nodes, 3, 8), "hi": nd[:, 24:48].reshape(n_nodes, 3, 8), "child": nd[:, 48:56].view(np.uint32),
+            "leaf_rec": rec[: n_leaves * k * 4].reshape(n_leaves, k // 2, 2, 4), "leaf_id": ids[: n_leaves * k].reshape(n_leaves, k),
+            "always": always[:n_always], "flat": flat[: n_pairs * 8].reshape(n_pairs, 2, 4)}
 
 
 def make_options(device: int = -1, rank: int = 0, world: int = 1, band_rows: int = 1, variant: int = RT_VARIANT_AUTO,
@@ -355,6 +373,19 @@ def render_linear(scene: Scene, opts: Optional[rt_options] = None):
     out = np.empty((rows, scene.c.width, 3), dtype=np.float32)
     st = rt_stats()
     _check(lib().rtb200_render_linear_f32(C.byref(scene.c), C.byref(opts) if opts is not None else None, out.ctypes.data, C.byref(st)))
+    return out, st.as_dict()
+
+
+def device_count() -> int:
+    return int(lib().rtb200_device_count())
+
+
+def render_rgb8_multi(scene: Scene, n_gpus: int = 0, opts: Optional[rt_options] = None, out: Optional[np.ndarray] = None):
+    """One process, n_gpus devices (0 = all): rtb200_render_rgb8_multi. Returns (uint8 [h,w,3], stats dict)."""
+    if out is None:
+        out = np.empty((scene.c.height, scene.c.width, 3), dtype=np.uint8)
+    st = rt_stats()
+    _check(lib().rtb200_render_rgb8_multi(C.byref(scene.c), C.byref(opts) if opts is not None else None, int(n_gpus), out.ctypes.data, C.byref(st)))
     return out, st.as_dict()
 
 
@@ -382,6 +413,11 @@ class ResidentScene:
         st = rt_stats()
         _check(lib().rtb200_render_device_wait(self.h, C.byref(st)))
         return st.as_dict()
+
+    def kernel_info(self) -> dict:
+        ki = rt_kernel_info()
+        _check(lib().rtb200_scene_kernel_info(self.h, C.byref(ki)))
+        return ki.as_dict()
 
     def release(self):
         if self.h:

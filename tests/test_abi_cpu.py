@@ -26,14 +26,14 @@ def test_library_exports_every_declared_symbol(repo):
     for s in syms:
         assert hasattr(L, s), f"librtb200.so does not export {s}"
     assert sorted(R.ABI_SYMBOLS) == syms
-    assert L.rtb200_abi_version() == 1
+    assert L.rtb200_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(R.rt_vec3) == 24 and C.sizeof(R.rt_camera) == 96 and C.sizeof(R.rt_sphere) == 64
-    assert C.sizeof(R.rt_image) == 24 and C.sizeof(R.rt_sky) == 32
-    assert C.sizeof(R.rt_scene) == 16 + 96 + 32 + 16 + 16 + 8
-    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 88
+    assert C.sizeof(R.rt_image) == 32 and C.sizeof(R.rt_sky) == 40
+    assert C.sizeof(R.rt_scene) == 16 + 96 + 40 + 16 + 16 + 8
+    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 104 and C.sizeof(R.rt_kernel_info) == 136
 
 
 @pytest.mark.parametrize("args", [
@@ -115,3 +115,27 @@ def test_invalid_scenes_are_rejected_before_touching_the_device():
     with pytest.raises(R.RtError) as e:
         R.render_rgb8(scenes.cover_scene(16, 12, 1), R.make_options(rank=2, world=2))
     assert e.value.code == -1
+
+
+def test_multi_gpu_entry_point_validates_before_touching_the_device():
+    sc = scenes.cover_scene(16, 12, 1)
+    with pytest.raises(R.RtError) as e:
+        R.render_rgb8_multi(sc, 2, R.make_options(rank=1, world=2))     # the call shards the frame itself
+    assert e.value.code == -1
+    sc.c.samples_per_pixel = 0
+    with pytest.raises(R.RtError) as e:
+        R.render_rgb8_multi(sc, 0)
+    assert e.value.code == -1
+
+
+def test_texture_buffer_size_is_checked():
+    """rt_image.bytes (ABI 2): the callee reads width*height*3 bytes, so a smaller buffer is rejected (the reference would
+    panic on the first out-of-bounds texel instead)."""
+    img = np.zeros((4, 4, 3), np.uint8)
+    cfg = scenes._variant(scenes.cover_config(), 16, 12, 1, 2)
+    sc = R.Scene.from_config(cfg)
+    sc.c.sky.mode = R.RT_SKY_TEXTURE
+    sc.c.sky.tex = R.rt_image(img.ctypes.data, 8, 8, img.size)          # claims 8x8, holds 4x4
+    with pytest.raises(R.RtError) as e:
+        R.render_rgb8(sc)
+    assert e.value.code == -1 and "bytes" in str(e.value)

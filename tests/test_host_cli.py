@@ -100,3 +100,45 @@ def test_cli_renders_the_same_png_as_the_python_host(tmp_path, which):
     png = np.asarray(Image.open(out))
     ref, _ = R.render_rgb8(R.Scene.from_config(cfg, scenes.SCENES_DIR))
     assert png.shape == (cfg["height"], cfg["width"], 3) and np.array_equal(png, ref)
+
+
+def test_jpeg_decoder_survives_malformed_headers(tmp_path):
+    """load_texture_image runs on scene-named files: malformed segments must produce an error (the reference's jpeg-decoder
+    crate returns Err and the caller panics cleanly), never an out-of-bounds read. Mutates the header bytes of a small
+    baseline JPEG (lengths, table ids, precisions, dimensions, truncations) and decodes every mutant."""
+    import ctypes as C
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    img = Image.fromarray(rng.integers(0, 255, (24, 40, 3), dtype=np.uint8), "RGB")
+    buf = io.BytesIO(); img.save(buf, format="JPEG", quality=80, subsampling=2); good = buf.getvalue()
+    sos = good.index(b"\xff\xda")
+    L = R.lib()
+
+    def decode(data):
+        p = tmp_path / "m.jpg"; p.write_bytes(data)
+        out = C.c_void_p(); w = C.c_uint64(); h = C.c_uint64()
+        rc = L.rtb200_decode_jpeg_file(str(p).encode(), C.byref(out), C.byref(w), C.byref(h))
+        if rc == 0:
+            assert 0 < w.value <= 65535 and 0 < h.value <= 65535
+            L.rtb200_free(out)
+        return rc
+
+    assert decode(good) == 0
+    n_err = 0
+    for trial in range(300):
+        d = bytearray(good)
+        kind = trial % 4
+        if kind == 0:                                   # one random header byte
+            d[int(rng.integers(2, sos + 14))] = int(rng.integers(0, 256))
+        elif kind == 1:                                 # a segment length set to something tiny / huge
+            pos = [i for i in range(2, sos) if d[i] == 0xFF and d[i + 1] not in (0x00, 0xFF)]
+            k = pos[int(rng.integers(len(pos)))]
+            d[k + 2], d[k + 3] = [(0, 0), (0, 1), (0, 2), (0, 3), (255, 255), (0, int(rng.integers(4, 40)))][int(rng.integers(6))]
+        elif kind == 2:                                 # truncation
+            d = d[: int(rng.integers(4, len(d)))]
+        else:                                           # several random header bytes
+            for _ in range(4):
+                d[int(rng.integers(2, sos + 14))] = int(rng.integers(0, 256))
+        n_err += decode(bytes(d)) != 0
+    assert n_err > 50

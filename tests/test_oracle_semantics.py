@@ -17,7 +17,7 @@ def _img(w, h):
 
 
 def _albedo(img, w, h, h_offset, u, v):
-    im = R.rt_image(img.ctypes.data, w, h)
+    im = R.rt_image(img.ctypes.data, w, h, img.size)
     out = (C.c_float * 3)()
     oob = O.lib().oracle_texture_albedo(C.byref(im), h_offset, u, v, out)
     return [out[0], out[1], out[2]], oob
@@ -41,7 +41,7 @@ def test_sky_texture_addressing_and_black_sky():
     img = _img(w, h)
     sc = R.Scene.from_config(base_config(8, 8, 1, 2, [], sky="gradient"))
     sc.c.sky.mode = R.RT_SKY_TEXTURE
-    sc.c.sky.tex = R.rt_image(img.ctypes.data, w, h)
+    sc.c.sky.tex = R.rt_image(img.ctypes.data, w, h, img.size)
     out = (C.c_float * 3)()
     O.lib().oracle_ray_color(C.byref(sc.c), R.vec3([0, 0, 0]), R.vec3([0, 1, 0]), 2, 2, out)      # straight up: t = 1, u = 0.5
     x, y = int(np.float32(0.5) * np.float32(w - 1)), 0

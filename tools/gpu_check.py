@@ -20,7 +20,7 @@ def cmp(name, sc, variant=0):
 sc = scenes.cover_scene(200, 150, 8)
 cmp("cover200x150x8", sc, R.RT_VARIANT_EXACT_F64)
 cmp("cover200x150x8", sc, R.RT_VARIANT_FILTERED)
-cmp("cover200x150x8", sc, R.RT_VARIANT_LANES)
+cmp("cover200x150x8", sc, R.RT_VARIANT_BRUTE_FORCE)
 sc = scenes.cover_scene(64, 48, 4, depth=3)
 cmp("cover64x48 depth3", sc, R.RT_VARIANT_FILTERED)
 if len(sys.argv) > 1 and sys.argv[1] == 'time':

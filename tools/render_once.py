@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Render a BASELINE config resident N times (profiling target). usage: render_once.py [C2] [reps] [variant]"""
+"""Render a BASELINE config resident N times (profiling / timing target). usage: render_once.py [C2] [reps] [variant]"""
 import sys, os
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, 'rust-raytracer_b200'))
@@ -15,7 +15,12 @@ if 'x' in name:
 else:
     sc = scenes.scene(name)
 rs = R.ResidentScene(sc, R.make_options(variant=variant))
+ki = rs.kernel_info()
+print(f"{name}: {ki['name']} regs={ki['registers']} local={ki['local_bytes']} smem={ki['smem_bytes']} grid={ki['grid']} ({ki['ctas_per_sm']}/SM) smem_mask={ki['smem_mask']} "
+      f"bvh nodes={ki['bvh_nodes']} leaves={ki['bvh_leaves']} depth={ki['bvh_depth']}", flush=True)
 out = torch.empty(sc.c.height * sc.c.width * 3, dtype=torch.uint8, device='cuda')
 for i in range(reps):
     st = rs.render(out.data_ptr())
-    print(f"{name}: rays={st['rays']} device_ms={st['device_ms']:.3f} trace_ms={st['trace_ms']:.3f} Mrays/s={st['rays']/st['device_ms']/1e3:.1f} cand/ray={st['candidates']/max(st['rays'],1):.2f} clusters/ray={st['clusters']/max(st['rays'],1):.2f}", flush=True)
+    r = max(st['rays'], 1)
+    print(f"{name}: rays={st['rays']} device_ms={st['device_ms']:.3f} trace_ms={st['trace_ms']:.3f} Mrays/s={st['rays']/st['device_ms']/1e3:.1f} "
+          f"f64tests/ray={st['candidates']/r:.2f} leaves/ray={st['clusters']/r:.2f} nodes/ray={st['nodes']/r:.2f}", flush=True)
