@@ -127,6 +127,24 @@ def host_threads():
     return len(aff), max(1, len(cores))
 
 
+def cgroup_cpu_limit():
+    """CPU bandwidth limit of this container in cores (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()
+        return None if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            q = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            per = float(f.read())
+        return None if q <= 0 else q / per
+    except (OSError, ValueError):
+        return None
+
+
 CPU_ARM_ENV = "RTB200_CPU_ARM_ENV"
 
 
@@ -136,7 +154,7 @@ def cpu_arm_env() -> dict:
     n_threads, _ = host_threads()
     env = dict(os.environ)
     env.update({"OMP_NUM_THREADS": str(n_threads), "OMP_PROC_BIND": "spread", "OMP_PLACES": "cores", "OMP_DYNAMIC": "false",
-                CPU_ARM_ENV: "1"})
+                "OMP_WAIT_POLICY": "passive", CPU_ARM_ENV: "1"})   # passive: idle threads must not burn a container's CPU quota spinning
     return env
 
 
@@ -161,16 +179,27 @@ def cpu_arm(cfg_name: str, steps: int, warmup: int, budget_s: float) -> dict:
     cfg = scenes.config(cfg_name)
     full_spp = cfg["samples_per_pixel"]
     n_threads, n_cores = host_threads()
+    quota = cgroup_cpu_limit()
     cal_cfg = dict(cfg); cal_cfg["samples_per_pixel"] = 1
     sc, O = _cpu_scene(cal_cfg)
-    counts = sorted({n_cores, n_threads})
-    rates = {}
-    for _ in range(2):                         # second pass: caches and the OpenMP pool are warm
-        for t in counts:
-            _, _, st = O.render(sc, linear=False, rgb8=True, threads=t)
-            rates[t] = max(rates.get(t, 0.0), st["rays"] / (st["render_ms"] / 1e3))
-    threads = max(rates, key=rates.get)
+    # candidate thread counts: one per physical core, every hardware thread and - when the container has a CPU bandwidth
+    # limit below that - the limit itself (more runnable threads than quota only adds throttling)
+    counts = {n_cores, n_threads}
+    if quota is not None and quota < n_threads:
+        counts |= {max(1, min(n_threads, int(quota + 0.5))), max(1, min(n_threads, int(2 * quota + 0.5)))}
+    counts = sorted(counts)
+    _, _, st = O.render(sc, linear=False, rgb8=True, threads=counts[0])        # warm caches and the OpenMP pool
     rays_per_spp = st["rays"]
+    rates = {}
+    for t in counts:
+        # sustained rate: ~1.5 s per candidate (a burst of a few ms does not show CPU-quota throttling)
+        quick = st["rays"] / max(st["render_ms"] / 1e3, 1e-6)
+        cal_spp = int(max(1, min(full_spp, 1.5 * quick / max(rays_per_spp, 1))))
+        c2 = dict(cfg); c2["samples_per_pixel"] = cal_spp
+        sc_t, _ = _cpu_scene(c2)
+        _, _, s2 = O.render(sc_t, linear=False, rgb8=True, threads=t)
+        rates[t] = s2["rays"] / (s2["render_ms"] / 1e3)
+    threads = max(rates, key=rates.get)
     per_step = budget_s / max(steps + warmup, 1)
     spp = int(max(1, min(full_spp, per_step * rates[threads] / max(rays_per_spp, 1))))
     run_cfg = dict(cfg); run_cfg["samples_per_pixel"] = spp
@@ -189,7 +218,7 @@ def cpu_arm(cfg_name: str, steps: int, warmup: int, budget_s: float) -> dict:
         "sample": f"{workload_string(cfg_name, cfg)}: each step renders {spp} of {full_spp} spp ({rays // max(steps, 1)} rays, {secs / max(steps, 1):.1f} s/step, "
                   f"{steps} steps); C++ restatement of the reference rayon row loop (OpenMP schedule(dynamic,1), g++ -O3 -ffp-contract=off), "
                   f"{threads} threads pinned (OMP_PROC_BIND=spread OMP_PLACES=cores) on {n_cores} cores / {n_threads} hardware threads; "
-                  f"calibration at 1 spp, Mrays/s: {cal}",
+                  f"{'no cgroup CPU limit' if quota is None else f'cgroup CPU limit {quota:.1f} cores'}; sustained calibration (~1.5 s each), Mrays/s: {cal}",
     }
 
 
@@ -312,50 +341,39 @@ def run_ours(args):
     value = total_rays / (dev_ms / 1e3) / 1e6
 
     # ---------------- e2e: host buffers through the C ABI, copies inside the timed region ----------------
-    opts = R.make_options(device=local, rank=rank, world=world, band_rows=1)
-    rows_max = RD.padded_rows(h, world, 1)
+    # The call a user makes: ONE blocking C-ABI call with the scene in host memory and the RGB8 frame delivered to host memory.
+    # 1 GPU: rtb200_render_rgb8. N GPUs: rtb200_render_rgb8_multi from ONE process (rank 0; the other ranks idle at the barrier):
+    # scene upload to every device (H2D), trace + resolve on every device, peer copies of the shards into the frame on device 0,
+    # one D2H. Every step pays all of it.
     host_frame = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
-    shard_dev = torch.zeros((rows_max, w, 3), dtype=torch.uint8, device=dev)
-    gbuf = torch.empty((world, rows_max, w, 3), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
-    frame_dev = torch.empty((h, w, 3), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
+    flushes = [torch.empty(160 << 20, dtype=torch.uint8, device=torch.device("cuda", i)) for i in range(world)] if (rank == 0 and world > 1) else [flush]
     h2d = d2h = 0
-    n_sph = scene.n_spheres
-    scene_bytes = ((n_sph + 1) // 2) * 32 + n_sph * 64 + 24
 
     def step_e2e():
         nonlocal h2d, d2h
-        flush.zero_()
+        for fb in flushes:
+            fb.zero_()
         if world == 1:
-            _, st = R.render_rgb8(scene, opts, out=host_frame.numpy())     # upload + render + D2H inside the call
-            h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
-            return st
-        rs = R.ResidentScene(scene, opts)                                   # H2D: scene records, every step
-        st = rs.render(shard_dev.data_ptr(), 0, RD._torch_stream())
-        RD.gather_frame(shard_dev, h, world, 1, rank, frame_dev, gbuf)     # NCCL gather to rank 0
-        if rank == 0:
-            host_frame.copy_(frame_dev, non_blocking=True)                  # D2H: the RGB8 frame
-        torch.cuda.synchronize()
-        rs.release()
-        h2d, d2h = scene_bytes, (h * w * 3 if rank == 0 else 0)
+            _, st = R.render_rgb8(scene, R.make_options(device=local), out=host_frame.numpy())   # upload + render + D2H inside the call
+        else:
+            _, st = R.render_rgb8_multi(scene, world, R.make_options(device=0), out=host_frame.numpy())
+            assert st["gpus_used"] == world
+        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
         return st
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_e2e()
+    rdr.wait()
     barrier()
-    t0 = time.perf_counter()
-    e_rays = 0
-    for _ in range(args.steps):
-        e_rays += step_e2e()["rays"]
+    e_rays = 0; e_wall = 0.0
+    if rank == 0:
+        for _ in range(max(1, min(args.warmup, 3))):
+            step_e2e()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e_rays += step_e2e()["rays"]
+        e_wall = time.perf_counter() - t0
     barrier()
-    e_wall = time.perf_counter() - t0
-    te = torch.tensor([e_wall, float(e_rays)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = te.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = te.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        e_wall, e_total = float(mx[0]), float(sm[1])
-    else:
-        e_total = float(e_rays)
-    e2e_value = e_total / e_wall / 1e6
+    e2e_value = (e_rays / e_wall / 1e6) if rank == 0 else 0.0
 
     # ---------------- golden: the timed frame (or, for configs the CPU oracle cannot finish, the same scene at the
     # committed reduced size rendered by the same N-GPU renderer) against the ORACLE's SHA-256 (tests/golden/frames.json) ----
@@ -394,15 +412,21 @@ def run_ours(args):
 
     n = scene.n_spheres
     hbm_peak, peak_src, sm_max = measured_peaks()
-    traffic = None
-    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram__bytes_read+write of one trace launch, from the committed ncu --set full capture
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("config") == args.config and world == 1:
-            traffic = tj.get("dram_bytes_per_launch")
-    rays_per_launch = rays / args.steps            # rank 0's trace launch
-    t_launch = (trace_ms / args.steps) / 1e3
+    # ncu-measured numbers of the trace kernel (profiles/kernel_profile.json, made by tools/ncu_profile_json.py from one
+    # `ncu --set full` capture): reported ONLY when the capture is of the build that is running (same registers, shared
+    # memory and grid) and of this config; otherwise null - a stale profile is worse than none.
+    ki = rdr.resident.kernel_info()
+    prof = None
+    ppath = os.path.join(REPO, "profiles", "kernel_profile.json")
+    if os.path.exists(ppath) and world == 1:
+        with open(ppath) as f:
+            pj = json.load(f).get(args.config.upper())
+        if pj and (pj["registers"], pj["smem_bytes"], pj["grid"]) == (ki["registers"], ki["smem_bytes"], ki["grid"]):
+            prof = pj
+    traffic = prof["dram_bytes_per_launch"] if prof else None
+    batches = max(int(st["batches"]), 1)
+    rays_per_launch = rays / args.steps / batches  # rank 0's trace launches (a frame is `batches` launches of equal size)
+    t_launch = (trace_ms / args.steps / batches) / 1e3
     achieved = rays_per_launch * ALG_BYTES_PER_RAY / t_launch / 1e9
     flops = rays_per_launch * (FLOP_PER_SPHERE_TEST * n + FLOP_PER_RAY_FIXED) / t_launch / 1e12
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
@@ -415,19 +439,28 @@ def run_ours(args):
                    "l2": "flushed (160 MiB device write > 126 MB L2) between steps, inside the timed region",
                    "timing": "CUDA events bracketing the K frames (frame streams joined before the end event), max over ranks", "pipelining": "consecutive frames alternate two streams / work-buffer sets: frame k+1 starts while frame k drains, resolves and is gathered", "wall_ms_per_step": wall_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e_wall / args.steps * 1e3, "path": "rtb200_render_rgb8 (C ABI), pinned host frame" if world == 1 else "per step: rtb200_scene_upload (H2D) + rtb200_render_device + NCCL gather + D2H of the frame on rank 0"},
+                "ms_per_step": e_wall / args.steps * 1e3, "path": "rtb200_render_rgb8 (C ABI), pinned host frame" if world == 1 else f"rtb200_render_rgb8_multi (C ABI) over {world} GPUs from one process: scene H2D to every device, trace, peer copies into the frame on device 0, one D2H"},
         "gpu_launches": int(total_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "kernel": "rt_wavefront_kernel<256,false,false,true>", "peak_source": peak_src,
-                     "note": f"algorithmic {ALG_BYTES_PER_RAY:.0f} B/ray (SURVEY §8d wavefront record) x rays per launch; the kernel keeps ray state in shared memory, "
-                             "so HBM is not the binding resource (traffic = ncu dram bytes of one launch) - the binding one is FP32 issue, see fp32_issue",
-                     "kernel_ms_per_launch": t_launch * 1e3, "kernel_share_of_step": (trace_ms_max / args.steps) / step_ms},
+                     "traffic": traffic, "kernel": ki["name"], "peak_source": peak_src,
+                     "binding_resource": "instruction issue / latency of the SM (the kernel keeps ray state in shared memory: real DRAM traffic is ~1 % of the HBM roofline, see dram_pct_of_peak)",
+                     "issue_active_pct": prof["issue_active_pct"] if prof else None, "lanes_per_inst": prof["lanes_per_inst"] if prof else None,
+                     "barrier_stall_pct": prof["barrier_stall_pct"] if prof else None, "dram_pct_of_peak": prof["dram_pct_of_peak"] if prof else None,
+                     "warps_active_pct": prof["warps_active_pct"] if prof else None,
+                     "profile": (f"profiles/kernel_profile.json[{args.config.upper()}] <- {prof['source']}" if prof else "no ncu capture of this build/config committed"),
+                     "kernel_registers": ki["registers"], "kernel_smem_bytes": ki["smem_bytes"], "kernel_grid": ki["grid"], "ctas_per_sm": ki["ctas_per_sm"],
+                     "note": f"frac = algorithmic {ALG_BYTES_PER_RAY:.0f} B/ray (SURVEY §8d: f64 wavefront ray record, 68 B read + 68 B written) x rays per launch / kernel time / measured HBM peak, "
+                             "as SURVEY §8d defines it; it is a nominal figure: HBM does not bind this kernel",
+                     "kernel_ms_per_launch": t_launch * 1e3, "launches_per_step": batches,
+                     "kernel_share_of_step": (trace_ms_max / args.steps) / step_ms,
+                     "kernel_share_note": "sum of the trace kernels' event times over the step time; > 1 when consecutive frames overlap on the two streams"},
         "fp32_issue": {"achieved": flops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / fp32_peak,
                        "flop_per_ray": FLOP_PER_SPHERE_TEST * n + FLOP_PER_RAY_FIXED,
                        "note": "reference-algorithm FLOPs (17 per sphere test x ALL spheres + 150 per ray, SURVEY §8d) over nominal FP32 vector peak 148 SM x 128 lanes x 2 x max SM clock; the kernel culls most sphere tests, so executed FLOPs are lower than credited"},
         "clocks": clocks, "golden": golden["status"], "golden_detail": golden,
         "rays_per_step": total_rays / args.steps, "candidates_per_ray": cand / max(rays, 1),
-        "algorithm": "two-level conservative f32 culling (clusters of 4 spheres) + exact f64 confirmation; identical results to the linear scan",
+        "algorithm": f"warp-cooperative traversal of an 8-wide BVH ({ki['bvh_nodes']} nodes, {ki['bvh_leaves']} leaves, depth {ki['bvh_depth']}) with conservative f32 slab / sphere tests + exact f64 confirmation; results identical to the reference's linear scan",
+        "bvh_nodes_per_ray": st["nodes"] / max(st["rays"], 1), "bvh_leaves_per_ray": st["clusters"] / max(st["rays"], 1),
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args.config, args.cpu_seconds)

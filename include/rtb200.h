@@ -133,6 +133,7 @@ typedef struct {
     uint32_t smem_bytes, grid, block, ctas_per_sm;
     uint32_t smem_mask;                    /* bit0 hierarchy, bit1 exact geometry, bit2 materials staged into shared memory */
     uint32_t bvh_nodes, bvh_leaves, bvh_depth;
+    uint32_t pool_slots;                   /* ray slots per CTA */
     char     name[96];
 } rt_kernel_info;
 

@@ -144,6 +144,7 @@ struct rtb200_scene_t {
     TraceParams tp{};
     rt_options opts{};
     uint32_t mode = MODE_TREE;
+    uint32_t slots_per_cta = kBlock;     // ray slots per CTA (one per thread)
     int minb = 3;
     int grid = 0;
     int ctas_per_sm = 0;
@@ -390,18 +391,20 @@ static int scene_upload_records(const rt_scene* s, const rt_options& opts, uint3
     tp.rows_local = rtb200_shard_rows(s->height, opts.rank, opts.world, opts.band_rows);
     tp.npix_local = tp.rows_local * s->width;
 
-    // ---- launch geometry: persistent grid = SMs x resident CTAs. What goes to shared memory next to the ray pool, the
-    // per-ray constants and the work lists, in order of value: the hierarchy (read at every step), exact geometry (every f64
-    // test), materials (once per hit). The richest set that keeps the targeted residency wins; RTB200_WF_SMEM=<mask> overrides
-    // (bit0 hierarchy, bit1 geo, bit2 mat) and RTB200_WF_MINB=<2|3> pins the register budget, for tuning experiments.
+    // ---- launch geometry: persistent grid = SMs x resident CTAs ----
+    // RTB200_WF_SMEM=<mask> (bit0 hierarchy / flat records, bit1 geo, bit2 mat in shared memory) and RTB200_WF_MINB=<2|3|4>
+    // pin the tuning knobs for experiments.
+    const char* es = getenv("RTB200_WF_SMEM");
     {
-        const char* es = getenv("RTB200_WF_SMEM");
+        // What could be staged into shared memory next to the ray pool: the hierarchy, exact geometry, materials. Measured in
+        // round 2: for scenes this small a larger L1 beats the staging, so "nothing staged" is tried first.
         const char* eb = getenv("RTB200_WF_MINB");
-        const uint32_t masks[] = {7u, 3u, 1u, 0u};
+        const uint32_t masks[] = {0u, 7u, 3u, 1u};   // measured (round 2): a larger L1 beats staging the small scenes' records
         bool found = false;
-        for (int minb : {3, 2}) {
+        for (int minb : {4, 3, 2}) {
+            if (minb == 4 && !(eb && atoi(eb) == 4)) continue;   // the 64-register build: only on request
             if (eb && atoi(eb) != minb) continue;
-            for (int need : {minb, 1}) {
+            for (int need : {std::max(1, minb * 256 / kBlock), 1}) {   // CTAs per SM this register budget is built for
                 for (uint32_t mask : masks) {
                     if (found) break;
                     if (es && (uint32_t)atoi(es) != mask) continue;
@@ -413,11 +416,12 @@ static int scene_upload_records(const rt_scene* s, const rt_options& opts, uint3
                     h->minb = minb; h->smem = sm; tp.scene_in_smem = mask; h->ctas_per_sm = occ; h->grid = ctx->sm_count * occ;
                     found = true;
                 }
-                if (found || minb == 3) break;   // the 80-register build is only worth it at full residency
+                if (found || minb >= 3) break;   // the 80 / 64-register builds are only worth it at full residency
             }
             if (found) break;
         }
         if (!found) return fail(RT_ERR_UNSUPPORTED, "no launch configuration fits shared memory");
+        h->slots_per_cta = kBlock;
     }
 
     // ---- per-sample staging: samples per batch bounded by the buffer cap ----
@@ -456,7 +460,8 @@ int rtb200_scene_kernel_info(rtb200_scene_handle h, rt_kernel_info* out) {
     memset(out, 0, sizeof *out);
     KernelInfo ki{};
     CU(wavefront_info(h->mode, h->tp.n_lights > 0, h->minb, &ki));
-    out->registers = ki.registers; out->local_bytes = ki.local_bytes; out->smem_bytes = (uint32_t)h->smem; out->grid = (uint32_t)h->grid; out->block = (uint32_t)kBlock;
+    out->registers = ki.registers; out->local_bytes = ki.local_bytes; out->smem_bytes = (uint32_t)h->smem; out->grid = (uint32_t)h->grid;
+    out->block = (uint32_t)kBlock; out->pool_slots = h->slots_per_cta;
     out->ctas_per_sm = (uint32_t)h->ctas_per_sm; out->smem_mask = h->tp.scene_in_smem;
     out->bvh_nodes = h->tp.n_nodes; out->bvh_leaves = h->tp.n_leaves; out->bvh_depth = h->tp.depth;
     snprintf(out->name, sizeof out->name, "%s", ki.name);
@@ -478,7 +483,7 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
 
     const uint32_t spp = tp.spp, spb = h->spp_batch;
     const uint32_t n_batches = (spp + spb - 1) / spb;
-    const uint32_t threads_total = (uint32_t)h->grid * (uint32_t)kBlock;
+    const uint32_t threads_total = (uint32_t)h->grid * h->slots_per_cta;   // ray slots of the whole grid: columns of the per-slot global arrays
 
     CU(W.samplebuf.ensure((size_t)spb * tp.npix_local * 16));
     CU(W.accum.ensure((size_t)tp.npix_local * 12));

@@ -8,7 +8,10 @@
 
 namespace rtk {
 
-constexpr int kBlock = 256;        // threads (= ray slots) per CTA of the trace kernel
+#ifndef RT_BLOCK
+#define RT_BLOCK 256
+#endif
+constexpr int kBlock = RT_BLOCK;   // threads (= ray slots) per CTA of the trace kernel
 #ifndef RT_LEAF_K
 #define RT_LEAF_K 8
 #endif
@@ -16,13 +19,13 @@ constexpr int kLeafK = RT_LEAF_K;  // sphere slots per BVH leaf            (= rt
 constexpr int kNodeVec = 14;       // float4 per 8-wide BVH node (224 B)   (= rtbvh::kNodeFloats / 4)
 // per-warp work lists of the closest-hit stage (entries: id << 5 | ray lane)
 #ifndef RT_CAP_IN
-#define RT_CAP_IN 320
+#define RT_CAP_IN 192
 #endif
 #ifndef RT_CAP_LF
-#define RT_CAP_LF 256
+#define RT_CAP_LF 160
 #endif
 #ifndef RT_CAP_CD
-#define RT_CAP_CD 128
+#define RT_CAP_CD 96
 #endif
 constexpr int kCapIn = RT_CAP_IN;   // (ray, inner node) pairs: LIFO stack; 7*depth+8 entries are reserved for single-entry descents
 constexpr int kCapLf = RT_CAP_LF;   // (ray, leaf) pairs

@@ -88,7 +88,7 @@ class rt_stats(C.Structure):
 class rt_kernel_info(C.Structure):
     _fields_ = [("registers", C.c_int32), ("local_bytes", C.c_int32), ("smem_bytes", C.c_uint32), ("grid", C.c_uint32),
                 ("block", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("smem_mask", C.c_uint32), ("bvh_nodes", C.c_uint32),
-                ("bvh_leaves", C.c_uint32), ("bvh_depth", C.c_uint32), ("name", C.c_char * 96)]
+                ("bvh_leaves", C.c_uint32), ("bvh_depth", C.c_uint32), ("pool_slots", C.c_uint32), ("name", C.c_char * 96)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(R.rt_vec3) == 24 and C.sizeof(R.rt_camera) == 96 and C.sizeof(R.rt_sphere) == 64
     assert C.sizeof(R.rt_image) == 32 and C.sizeof(R.rt_sky) == 40
     assert C.sizeof(R.rt_scene) == 16 + 96 + 40 + 16 + 16 + 8
-    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 104 and C.sizeof(R.rt_kernel_info) == 136
+    assert C.sizeof(R.rt_options) == 32 and C.sizeof(R.rt_stats) == 104 and C.sizeof(R.rt_kernel_info) == 140
 
 
 @pytest.mark.parametrize("args", [
