@@ -304,6 +304,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # A second, CPU-side process group: while rank 0 drives ALL GPUs from one process (e2e leg) the other ranks must wait
+    # without touching their GPUs - an NCCL barrier would spin in a kernel there and time-slice with rank 0's work.
+    host_pg = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_pg)
+
     def step_resident():
         flush.zero_()
         rdr.render_async()          # enqueue trace + resolve (+ NCCL gather): no host wait inside the timed region
@@ -362,7 +371,7 @@ def run_ours(args):
         return st
 
     rdr.wait()
-    barrier()
+    host_barrier()
     e_rays = 0; e_wall = 0.0
     if rank == 0:
         for _ in range(max(1, min(args.warmup, 3))):
@@ -372,7 +381,7 @@ def run_ours(args):
         for _ in range(args.steps):
             e_rays += step_e2e()["rays"]
         e_wall = time.perf_counter() - t0
-    barrier()
+    host_barrier()
     e2e_value = (e_rays / e_wall / 1e6) if rank == 0 else 0.0
 
     # ---------------- golden: the timed frame (or, for configs the CPU oracle cannot finish, the same scene at the

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rtb200_bvh.hpp"
@@ -77,6 +78,9 @@ struct DeviceCtx {
     // scene arenas of released handles, kept for the next upload (a per-frame upload costs no cudaMalloc / cudaFree)
     struct Arena { void* p; size_t cap; };
     std::vector<Arena> arena_cache;
+    std::vector<cudaEvent_t> event_pool;  // timing events of released handles (creating four events per one-shot render costs more than the upload)
+    struct OccKey { uint32_t mode; bool lights; int minb; size_t smem; int occ; };
+    std::vector<OccKey> occ_cache;        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers
     PinnedBuf staging;                    // host image of the arena being uploaded
     cudaEvent_t staging_free = nullptr;   // the last H2D copy out of `staging` has finished
 };
@@ -240,7 +244,7 @@ int rtb200_scene_release(rtb200_scene_handle h) {
         cudaSetDevice(h->device);
         if (h->pending_frames) render_collect(h, nullptr);   // frames still in flight read the scene arrays
         else if (h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
-        for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+        for (cudaEvent_t e : h->ev) h->ctx->event_pool.push_back(e);
         if (h->arena) {
             auto& cache = h->ctx->arena_cache;
             if (h->arena_cap <= (64u << 20) && cache.size() < 4) cache.push_back(DeviceCtx::Arena{h->arena, h->arena_cap});
@@ -411,7 +415,12 @@ static int scene_upload_records(const rt_scene* s, const rt_options& opts, uint3
                     if (h->mode == MODE_EXACT && (mask & 1u)) continue;
                     size_t sm = wavefront_smem_bytes(tp, h->mode, mask);
                     if (sm > ctx->max_smem) continue;
-                    int occ = wavefront_max_ctas_per_sm(h->mode, n_lights > 0, sm, minb);
+                    int occ = -1;
+                    for (auto& k : ctx->occ_cache) if (k.mode == h->mode && k.lights == (n_lights > 0) && k.minb == minb && k.smem == sm) occ = k.occ;
+                    if (occ < 0) {
+                        occ = wavefront_max_ctas_per_sm(h->mode, n_lights > 0, sm, minb);
+                        ctx->occ_cache.push_back(DeviceCtx::OccKey{h->mode, n_lights > 0, minb, sm, occ});
+                    }
                     if (occ < need || occ <= 0) continue;
                     h->minb = minb; h->smem = sm; tp.scene_in_smem = mask; h->ctas_per_sm = occ; h->grid = ctx->sm_count * occ;
                     found = true;
@@ -504,12 +513,16 @@ static int render_enqueue(rtb200_scene_handle h, void* dev_rgb8, void* dev_linea
     const uint32_t kRing = 64, per_frame = 2 + 2 * n_batches;
     if (h->pending_frames >= kRing) return fail(RT_ERR_INVALID, "more than 64 frames enqueued without rtb200_render_device_wait");
     while (h->ev.size() < (size_t)(h->pending_frames + 1) * per_frame) {
-        cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev.push_back(e);
+        cudaEvent_t e;
+        if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else CU(cudaEventCreate(&e));
+        h->ev.push_back(e);
     }
     cudaEvent_t* fev = h->ev.data() + (size_t)h->pending_frames * per_frame;
     unsigned long long* stat = (unsigned long long*)W.small.p;
     unsigned int* counters = (unsigned int*)((char*)W.small.p + 256);
     CU(cudaMemsetAsync(W.small.p, 0, 256 + (size_t)n_batches * 4, st));
+    CU(cudaMemsetAsync((char*)W.small.p + 64, 0xff, 16, st));   // stat[8], stat[9]: minima (kernel start / first dry-queue time, ns)
 
     tp.samplebuf = (float4*)W.samplebuf.p;
     tp.stack = (uint32_t*)W.stack.p;
@@ -553,11 +566,12 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
     cudaStream_t st = h->last_stream;
     DeviceCtx::WorkSet& W = ctx->ws[h->last_set];
     unsigned long long hstat[16] = {0}, herr[2] = {0, 0};
-    CU(cudaMemcpyAsync(hstat, W.small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
-    for (int i = 0; i < h->n_streams; ++i) CU(cudaStreamSynchronize(h->streams[i]));
+    for (int i = 0; i < h->n_streams; ++i) if (h->streams[i] != st) CU(cudaStreamSynchronize(h->streams[i]));
     h->n_streams = 0;
-    // error counters accumulate over every frame since the last wait (each frame ORs into them; nothing clears them in between)
-    CU(cudaMemcpy(herr, h->err, sizeof herr, cudaMemcpyDeviceToHost));
+    // error counters accumulate over every frame since the last wait (each frame adds to them; nothing clears them in between)
+    CU(cudaMemcpyAsync(hstat, W.small.p, sizeof hstat, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(herr, h->err, sizeof herr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (herr[0] | herr[1]) CU(cudaMemset(h->err, 0, sizeof herr));
     const uint32_t frames = h->pending_frames;
     h->pending_frames = 0;
@@ -575,6 +589,11 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats) {
         stats->device_ms = dv; stats->trace_ms = tr; stats->frames = frames;
         stats->rays = hstat[0]; stats->candidates = hstat[1]; stats->samples = hstat[3]; stats->clusters = hstat[4]; stats->nodes = hstat[6];
         stats->gpus_used = 1;
+        if (getenv("RTB200_PRINT_TAIL") && hstat[8] != ~0ull) {   // last batch of the last frame: when did the global queue run dry, when did the last CTA exit
+            const double total = (double)(hstat[10] - hstat[8]) * 1e-6, tail = hstat[9] != ~0ull ? (double)(hstat[10] - hstat[9]) * 1e-6 : 0.0;
+            fprintf(stderr, "[rtb200] trace kernel: first CTA start -> last CTA exit %.3f ms; queue dry -> last CTA exit (tail) %.3f ms; iterations after the queue ran dry: max %llu, mean %.1f per CTA\n",
+                    total, tail, hstat[11], (double)hstat[12] / std::max(1, h->grid));
+        }
         if (getenv("RTB200_PRINT_PHASES")) {
             fprintf(stderr, "[rtb200] fallbacks=%llu phases(warp-cycles): traverse=%llu exact=%llu waitA=%llu sort=%llu shade=%llu waitC=%llu warp_iters=%llu\n",
                     hstat[2], hstat[8], hstat[9], hstat[10], hstat[11], hstat[12], hstat[13], hstat[14]);
@@ -655,8 +674,11 @@ int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, floa
 }
 
 // One process, n_gpus devices: the reference's row bands (raytracer.rs:254-262) dealt round-robin to the devices (band b ->
-// device b mod G, like the torchrun flavour in rtb200/dist.py), every device renders its compact shard, the shards are
-// copied peer-to-peer over NVLink straight into their interleaved rows of the frame on device 0, ONE device->host copy.
+// device b mod G, like the torchrun flavour in rtb200/dist.py). The hierarchy is built once; one host thread per device
+// uploads the scene, enqueues trace + resolve, copies its compact shard peer-to-peer over NVLink straight into its interleaved
+// rows of the frame on the first device and waits for its stream; then ONE device->host copy.
+static std::mutex g_multi_mu;   // multi-GPU calls take turns (they share the frame buffer of the first device)
+
 int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32_t n_gpus, uint8_t* out_rgb8, rt_stats* stats) {
     if (!s || !out_rgb8) return fail(RT_ERR_INVALID, "null argument");
     auto wall0 = std::chrono::steady_clock::now();
@@ -674,59 +696,77 @@ int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32
     if (first >= count) return fail(RT_ERR_NO_DEVICE, "no such CUDA device");
     int G = n_gpus <= 0 ? count - first : std::min(n_gpus, count - first);
     const uint32_t bands = (s->height + base.band_rows - 1) / base.band_rows;
-    G = (int)std::min<uint32_t>((uint32_t)G, bands);
+    G = (int)std::min<uint32_t>((uint32_t)G, bands);   // a device needs at least one band
     if (G <= 1) { base.device = first; int r = render_host(s, &base, out_rgb8, nullptr, stats); if (r == RT_OK && stats) stats->gpus_used = 1; return r; }
 
     DeviceRestore restore;
+    std::lock_guard<std::mutex> multi_lock(g_multi_mu);
     rtbvh::Records R;
     rtbvh::build_records(s, mode_of(base.variant) == MODE_TREE, R);
-    std::vector<rtb200_scene_handle> hs((size_t)G, nullptr);
-    std::vector<std::unique_lock<std::recursive_mutex>> locks;
-    struct Cleanup { std::vector<rtb200_scene_handle>& v; ~Cleanup() { std::string keep = g_last_error; for (auto h : v) if (h) rtb200_scene_release(h); g_last_error = keep; } } cleanup{hs};
     const size_t row_bytes = (size_t)s->width * 3;
-    for (int g = 0; g < G; ++g) {            // ascending device order: two concurrent multi-GPU calls cannot deadlock
-        rt_options o = base; o.device = first + g; o.rank = g; o.world = G;
-        if ((rc = scene_upload_records(s, o, n_lights, R, &hs[g])) != RT_OK) return rc;
-        locks.emplace_back(hs[g]->ctx->mu);
+    // the frame lives on the first device; peers get access both ways once per process (without it the copies stage through the host)
+    DeviceCtx* c0 = nullptr;
+    if ((rc = get_ctx(first, &c0)) != RT_OK) return rc;
+    uint8_t* frame = nullptr;
+    {
+        std::lock_guard<std::recursive_mutex> lk(c0->mu);
+        CU(c0->frame.ensure((size_t)s->height * row_bytes + 16));
+        frame = (uint8_t*)c0->frame.p;
+        static bool peered[64] = {false};
+        for (int g = 1; g < G; ++g) {
+            if (peered[first + g]) continue;
+            cudaSetDevice(first); if (cudaDeviceEnablePeerAccess(first + g, 0) != cudaSuccess) cudaGetLastError();
+            cudaSetDevice(first + g); if (cudaDeviceEnablePeerAccess(first, 0) != cudaSuccess) cudaGetLastError();
+            peered[first + g] = true;
+        }
     }
-    DeviceCtx* c0 = hs[0]->ctx;
-    CU(cudaSetDevice(first));
-    CU(c0->frame.ensure((size_t)s->height * row_bytes + 16));
-    uint8_t* frame = (uint8_t*)c0->frame.p;
-    for (int g = 1; g < G; ++g) {            // peer access both ways (already-enabled is fine; without it the copies stage through the host)
-        cudaSetDevice(first); if (cudaDeviceEnablePeerAccess(first + g, 0) != cudaSuccess) cudaGetLastError();
-        cudaSetDevice(first + g); if (cudaDeviceEnablePeerAccess(first, 0) != cudaSuccess) cudaGetLastError();
-    }
-    std::vector<cudaEvent_t> done((size_t)G, nullptr);
-    struct EvCleanup { std::vector<cudaEvent_t>& v; int first; ~EvCleanup() { for (size_t g = 0; g < v.size(); ++g) if (v[g]) { cudaSetDevice(first + (int)g); cudaEventDestroy(v[g]); } } } evc{done, first};
-    for (int g = 0; g < G; ++g) {
-        DeviceCtx* c = hs[g]->ctx;
-        CU(cudaSetDevice(first + g));
-        const size_t rows = hs[g]->tp.rows_local;
-        CU(c->out_rgb8.ensure(rows * row_bytes + 16));
-        if ((rc = render_enqueue(hs[g], c->out_rgb8.p, nullptr, nullptr, 0)) != RT_OK) return rc;
-        // shard -> frame: full bands as one strided 2-D copy (a "row" of the copy = one band), then the partial last band
-        const size_t band_bytes = (size_t)base.band_rows * row_bytes;
-        const size_t full = rows / base.band_rows, rem = rows - full * base.band_rows;
-        if (full) CU(cudaMemcpy2DAsync(frame + (size_t)g * band_bytes, (size_t)G * band_bytes, c->out_rgb8.p, band_bytes, band_bytes, full, cudaMemcpyDefault, c->stream));
-        if (rem) CU(cudaMemcpyAsync(frame + ((size_t)full * G + g) * band_bytes, (uint8_t*)c->out_rgb8.p + full * band_bytes, rem * row_bytes, cudaMemcpyDefault, c->stream));
-        CU(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
-        CU(cudaEventRecord(done[g], c->stream));
-    }
-    CU(cudaSetDevice(first));
-    for (int g = 1; g < G; ++g) CU(cudaStreamWaitEvent(c0->stream, done[g], 0));
-    CU(cudaMemcpyAsync(out_rgb8, frame, (size_t)s->height * row_bytes, cudaMemcpyDeviceToHost, c0->stream));
+    struct Result { int rc = RT_OK; std::string err; rt_stats st{}; uint64_t h2d = 0; };
+    std::vector<Result> res((size_t)G);
+    auto worker = [&](int g) {
+        Result& r = res[(size_t)g];
+        auto body = [&]() -> int {
+            rt_options o = base; o.device = first + g; o.rank = g; o.world = G;
+            rtb200_scene_handle h = nullptr;
+            int rcw = scene_upload_records(s, o, n_lights, R, &h);
+            if (rcw != RT_OK) return rcw;
+            struct Rel { rtb200_scene_handle h; ~Rel() { std::string keep = g_last_error; rtb200_scene_release(h); g_last_error = keep; } } rel{h};
+            DeviceCtx* c = h->ctx;
+            std::lock_guard<std::recursive_mutex> lk(c->mu);
+            CU(cudaSetDevice(first + g));
+            const size_t rows = h->tp.rows_local;
+            CU(c->out_rgb8.ensure(rows * row_bytes + 16));
+            if ((rcw = render_enqueue(h, c->out_rgb8.p, nullptr, nullptr, 0)) != RT_OK) return rcw;
+            // shard -> frame: full bands as one strided 2-D copy (a "row" of the copy = one band), then the partial last band
+            const size_t band_bytes = (size_t)base.band_rows * row_bytes;
+            const size_t full = rows / base.band_rows, rem = rows - full * base.band_rows;
+            if (full) CU(cudaMemcpy2DAsync(frame + (size_t)g * band_bytes, (size_t)G * band_bytes, c->out_rgb8.p, band_bytes, band_bytes, full, cudaMemcpyDefault, c->stream));
+            if (rem) CU(cudaMemcpyAsync(frame + ((size_t)full * G + g) * band_bytes, (uint8_t*)c->out_rgb8.p + full * band_bytes, rem * row_bytes, cudaMemcpyDefault, c->stream));
+            if ((rcw = render_collect(h, &r.st)) != RT_OK) return rcw;   // waits for the stream: the shard is in the frame
+            r.h2d = h->h2d_bytes;
+            return RT_OK;
+        };
+        r.rc = body();
+        if (r.rc != RT_OK) r.err = g_last_error;
+    };
+    std::vector<std::thread> threads;
+    for (int g = 1; g < G; ++g) threads.emplace_back(worker, g);
+    worker(0);
+    for (auto& t : threads) t.join();
+    for (int g = 0; g < G; ++g) if (res[(size_t)g].rc != RT_OK) return fail(res[(size_t)g].rc, "device " + std::to_string(first + g) + ": " + res[(size_t)g].err);
     rt_stats total{};
     for (int g = 0; g < G; ++g) {
-        rt_stats st{};
-        if ((rc = render_collect(hs[g], &st)) != RT_OK) return rc;
+        const rt_stats& st = res[(size_t)g].st;
         total.rays += st.rays; total.samples += st.samples; total.candidates += st.candidates; total.clusters += st.clusters; total.nodes += st.nodes;
         total.device_ms = std::max(total.device_ms, st.device_ms); total.trace_ms = std::max(total.trace_ms, st.trace_ms);
         total.kernel_launches += st.kernel_launches; total.batches = std::max(total.batches, st.batches);
-        total.h2d_bytes += hs[g]->h2d_bytes;
+        total.h2d_bytes += res[(size_t)g].h2d;
     }
-    CU(cudaSetDevice(first));
-    CU(cudaStreamSynchronize(c0->stream));
+    {
+        std::lock_guard<std::recursive_mutex> lk(c0->mu);
+        CU(cudaSetDevice(first));
+        CU(cudaMemcpyAsync(out_rgb8, frame, (size_t)s->height * row_bytes, cudaMemcpyDeviceToHost, c0->stream));
+        CU(cudaStreamSynchronize(c0->stream));
+    }
     total.frames = 1; total.gpus_used = G;
     total.d2h_bytes = (size_t)s->height * row_bytes + (size_t)G * (128 + 16);
     total.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();

@@ -68,7 +68,7 @@ struct SceneRefs {
     const double4* geo; const DevMat* mat;
 };
 
-struct Stats { unsigned long long rays = 0, cand = 0, ovf = 0, samples = 0, leaves = 0, nodes = 0; };
+struct Stats { uint32_t rays = 0, cand = 0, ovf = 0, samples = 0, leaves = 0, nodes = 0; };   // per thread and launch: far below 2^32
 
 RT_DEV void bulk_stage(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     const uint32_t CH = 32768u;
@@ -387,9 +387,15 @@ RT_DEV bool regenerate_slot(const TraceParams& p, const Pool& P, bool want, uint
     unsigned my = base + __popc(need & ((1u << lane) - 1u));
     if (my >= p.total_work) return false;
     const uint32_t k0 = p.key0, k1 = p.key1;
-    uint32_t s_local = my / p.npix_local;
-    uint32_t lp = my - s_local * p.npix_local;
-    uint32_t y_local = lp / p.width, x = lp - y_local * p.width;
+    // Order of the global queue: image rows from the BOTTOM up, all samples of a row before the next row, x innermost.
+    // The long paths of these scenes start at the ground / the spheres; the rows handed out last are the top of the image -
+    // sky, one ray per sample - so that the stragglers of the last expensive rows finish under the cover of cheap work
+    // instead of holding nearly empty CTAs for ~50 iterations after the queue ran dry (0.5 ms per launch).
+    // The (pixel, sample) -> RNG stream and the samplebuf index do not depend on the order.
+    const uint32_t x = my % p.width, t_ = my / p.width;
+    const uint32_t s_local = t_ % p.s_count, rr = t_ / p.s_count;
+    const uint32_t y_local = p.rows_local - 1u - rr;
+    const uint32_t lp = y_local * p.width + x;
     uint32_t band = y_local / p.band_rows;
     uint32_t y = (band * (uint32_t)p.world + (uint32_t)p.rank) * p.band_rows + (y_local - band * p.band_rows);
     Rng rng; rng_init(rng, y * p.width + x, p.s0 + s_local);
@@ -400,7 +406,7 @@ RT_DEV bool regenerate_slot(const TraceParams& p, const Pool& P, bool want, uint
     D3 o, d;
     get_ray(p.cam, u, v, o, d);
     P.ox[s] = o.x; P.oy[s] = o.y; P.oz[s] = o.z; P.dx[s] = d.x; P.dy[s] = d.y; P.dz[s] = d.z;
-    P.work[s] = my; P.pix[s] = rng.pixel; P.smp[s] = rng.sample;
+    P.work[s] = s_local * p.npix_local + lp; P.pix[s] = rng.pixel; P.smp[s] = rng.sample;   // samplebuf index [sample][pixel]
     P.blk[s] = (rng.blk << 1) | rng.has; P.clo[s] = rng.c_lo; P.chi[s] = rng.c_hi;
     P.lvl[s] = 0u;
     if (LIGHTS) {
@@ -585,23 +591,20 @@ RT_DEV bool shade_slot(const TraceParams& p, const SceneRefs& sc, const Pool& P,
     return done;
 }
 
-RT_DEV void flush_stats(const TraceParams& p, Stats st, int lane) {
+RT_DEV void flush_stats(const TraceParams& p, const Stats& st, int lane) {
+    unsigned long long v[6] = {st.rays, st.cand, st.ovf, st.samples, st.leaves, st.nodes};
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        st.rays += __shfl_down_sync(0xffffffffu, st.rays, off);
-        st.cand += __shfl_down_sync(0xffffffffu, st.cand, off);
-        st.ovf += __shfl_down_sync(0xffffffffu, st.ovf, off);
-        st.samples += __shfl_down_sync(0xffffffffu, st.samples, off);
-        st.leaves += __shfl_down_sync(0xffffffffu, st.leaves, off);
-        st.nodes += __shfl_down_sync(0xffffffffu, st.nodes, off);
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
     }
     if (lane == 0) {
-        atomicAdd(&p.stat[0], st.rays);
-        atomicAdd(&p.stat[1], st.cand);
-        atomicAdd(&p.stat[2], st.ovf);
-        atomicAdd(&p.stat[3], st.samples);
-        atomicAdd(&p.stat[4], st.leaves);
-        atomicAdd(&p.stat[6], st.nodes);
+        atomicAdd(&p.stat[0], v[0]);
+        atomicAdd(&p.stat[1], v[1]);
+        atomicAdd(&p.stat[2], v[2]);
+        atomicAdd(&p.stat[3], v[3]);
+        atomicAdd(&p.stat[4], v[4]);
+        atomicAdd(&p.stat[6], v[5]);
     }
 }
 

@@ -1,7 +1,7 @@
 // rtb200_wavefront.cu — the barrier-synchronised wavefront trace kernel (round 1's structure with round 2's stages).
 //
 // One persistent CTA (256 threads) per resident slot of every SM owns a pool of 256 ray slots in shared memory. Until the
-// global (pixel,sample) queue is drained and the pool is empty, the CTA repeats three barrier-separated stages
+// global (pixel,sample) queue is drained and the pool is empty, the CTA repeats three stages (two barriers per iteration)
 // (rtb200_trace.cuh): closest-hit (thread t <-> slot t; warp-cooperative BVH traversal, or the linear scans of the
 // validation modes), a sort that compacts the live slots class by class with warp ballots (perm[]), and shade + ray-gen
 // (thread i <-> slot perm[i], so a warp shades one material).
@@ -21,7 +21,7 @@ struct WfSmem {
     uint32_t nodes_off, leafrec_off, leafid_off, filt_off, geo_off, mat_off;
     uint32_t warpctx;   // kWarpCtxBytes per warp (MODE_TREE)
     uint32_t pool;      // kSlotBytes * kBlock
-    uint32_t perm;      // uint16[kBlock]
+    uint32_t perm;      // uint16[5 classes][kBlock]: every class has its own segment, so a slot's position needs no other class's count
     uint32_t cnt;       // uint32[2][8]
     uint32_t total;
 };
@@ -39,7 +39,7 @@ __host__ __device__ inline WfSmem wf_layout(uint32_t n, uint32_t n_pairs, uint32
     off = (off + 15u) & ~15u;
     L.warpctx = off; if (mode == MODE_TREE) off += (uint32_t)(kBlock / 32) * kWarpCtxBytes;
     L.pool = off; off += kSlotBytes * (uint32_t)kBlock;
-    L.perm = off; off += kBlock * 2u;
+    L.perm = off; off += 5u * kBlock * 2u;
     L.cnt = off; off += 2u * 8u * 4u;
     L.total = off;
     return L;
@@ -93,8 +93,13 @@ __global__ void __launch_bounds__(kBlock, (MINB * 256 / kBlock) > 0 ? (MINB * 25
     }
     mbar_wait(bar, 0);
 
+    // frame-tail diagnostics (stat[8..10]): first CTA start, first moment a warp found the global queue dry, last CTA exit (ns)
+    auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (tid == 0) atomicMin(&p.stat[8], now_ns());
     Stats st;
     bool exhausted = false;   // warp-uniform: this warp has seen the end of the queue
+    bool stamped = false;
+    uint32_t dry_iters = 0;   // iterations of this CTA after it first found the global queue dry
     regenerate_slot<LIGHTS>(p, P, true, (uint32_t)tid, lane, exhausted, st);   // initial fill of the pool
     __syncthreads();
 
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kBlock, (MINB * 256 / kBlock) > 0 ? (MINB * 25
         const uint32_t cls = closest_hit<MODE>(p, sc, P, W, alive, (uint32_t)tid, lane, st);
 
         // =========================== sort: compact the live slots class by class ===========================
-        uint32_t wbase_c = 0, rank = 0;
+        // warp ballot + one shared-memory atomic per (warp, class) reserve positions in the class's own segment of perm[]
 #pragma unroll
         for (uint32_t c = 0; c < CLS_DEAD; ++c) {
             unsigned b = __ballot_sync(FULL, cls == c);
@@ -115,30 +120,29 @@ __global__ void __launch_bounds__(kBlock, (MINB * 256 / kBlock) > 0 ? (MINB * 25
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(b));
                 base = __shfl_sync(FULL, base, 0);
-                if (cls == c) { wbase_c = base; rank = __popc(b & lt_mask); }
+                if (cls == c) s_perm[c * (uint32_t)kBlock + base + (uint32_t)__popc(b & lt_mask)] = (uint16_t)tid;
             }
         }
-        __syncthreads();   // A: class counts complete (and every warp's closest-hit results are in the pool)
+        __syncthreads();   // A: class counts and perm complete (and every warp's closest-hit results are in the pool)
         uint32_t c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3], c4 = cnt[4];
         const uint32_t e0 = c0, e1 = e0 + c1, e2 = e1 + c2, e3 = e2 + c3, n_live = e3 + c4;   // class end offsets
-        if (cls != CLS_DEAD) {
-            uint32_t start = cls == 0 ? 0u : cls == 1 ? e0 : cls == 2 ? e1 : cls == 3 ? e2 : e3;
-            s_perm[start + wbase_c + rank] = (uint16_t)tid;
-        }
         if (tid < 8) s_cnt[((it + 1u) & 1u) * 8u + tid] = 0u;   // reset the other counter set for the next iteration
-        __syncthreads();   // B: perm complete
 
         // =========================== shade + regenerate: thread i <-> slot perm[i] ===========================
         const bool active = (uint32_t)tid < n_live;
-        const uint32_t s = active ? (uint32_t)s_perm[tid] : 0u;
         const uint32_t c = !active ? CLS_DEAD : ((uint32_t)tid < e0 ? CLS_MISS : (uint32_t)tid < e1 ? CLS_DIFFUSE : (uint32_t)tid < e2 ? CLS_METAL : (uint32_t)tid < e3 ? CLS_GLASS : CLS_LIGHT);
+        const uint32_t cstart = c == CLS_MISS ? 0u : c == CLS_DIFFUSE ? e0 : c == CLS_METAL ? e1 : c == CLS_GLASS ? e2 : e3;
+        const uint32_t s = active ? (uint32_t)s_perm[c * (uint32_t)kBlock + ((uint32_t)tid - cstart)] : 0u;
         bool done = false;
         if (active) done = shade_slot<LIGHTS>(p, sc, P, s, c);
         regenerate_slot<LIGHTS>(p, P, active && done, s, lane, exhausted, st);
+        if (exhausted && !stamped) { stamped = true; if (lane == 0) atomicMin(&p.stat[9], now_ns()); }
+        if (stamped) ++dry_iters;
         const bool still_alive = active && (P.lvl[s] != kDeadLevel);
         if (!__syncthreads_or(still_alive ? 1 : 0)) break;   // C: pool written back; exit when the CTA has no ray left
     }
     flush_stats(p, st, lane);
+    if (tid == 0) { atomicMax(&p.stat[10], now_ns()); atomicMax(&p.stat[11], (unsigned long long)dry_iters); atomicAdd(&p.stat[12], (unsigned long long)dry_iters); }
 }
 
 template <typename F>
