@@ -22,8 +22,7 @@ def line_of(path, needle, after=0):
 k_fill = line_of(WF, "initial fill of the pool")
 k_ch = line_of(WF, "closest_hit<MODE>(")
 k_sort = line_of(WF, "=== sort: compact")
-k_A = line_of(WF, "// A: class counts complete")
-k_B = line_of(WF, "// B: perm complete")
+k_A = line_of(WF, "// A: class counts and perm complete")
 k_shade = line_of(WF, "shade_slot<LIGHTS>(p, sc")
 k_regen = line_of(WF, "regenerate_slot<LIGHTS>(p, P, active && done")
 k_C = line_of(WF, "// C: pool written back")
@@ -35,8 +34,6 @@ def kernel_stage(l):
     if l == k_ch: return "closest_hit"
     if l < k_A: return "sort"
     if l == k_A: return "barrier_A"
-    if l < k_B: return "sort"
-    if l == k_B: return "barrier_B"
     if l <= k_shade: return "shade"
     if l == k_regen: return "regen"
     if l <= k_C: return "barrier_C"
@@ -101,7 +98,7 @@ rows = list(csv.reader(csvout.splitlines())); hdr = rows[1]; data = rows[2:]
 assert len(seq) == len(data), (len(seq), len(data))
 iex = hdr.index("Instructions Executed"); ismp = hdr.index("# Samples"); ithr = hdr.index("Thread Instructions Executed")
 stall = {h: i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h}
-order = ["setup", "regen", "ch_setup", "ch_control", "node_step", "leaf_step", "exact_step", "ch_merge", "sort", "barrier_A", "barrier_B", "shade", "barrier_C", "loop_ctl", "exit", "other"]
+order = ["setup", "regen", "ch_setup", "ch_control", "node_step", "leaf_step", "exact_step", "ch_merge", "sort", "barrier_A", "shade", "barrier_C", "loop_ctl", "exit", "other"]
 agg = collections.OrderedDict((k, [0, 0, 0, 0, collections.Counter()]) for k in order)
 tot = [0, 0]; bar = 0
 for ch, r in zip(seq, data):
