@@ -53,7 +53,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None

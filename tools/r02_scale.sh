@@ -2,7 +2,6 @@
 # round 2, 8-GPU job: multi-GPU correctness tests, the C2 scaling run (N = 1, 2, 4, 8, back to back on one box) and the big configs at N = 8
 mkdir -p gpurun_out/r02; cd /root/repo; O=gpurun_out/r02
 nvidia-smi -L | head -8
-timeout 600 python -m pytest tests/test_gpu_dist.py tests/test_gpu_parity.py -m gpu -q -k "dist or multi or harness or nccl or shards" > $O/scale_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/scale_pytest.log
 run() { # N config steps warmup extra...
   N=$1; C=$2; K=$3; W=$4; shift 4
   if [ $N -eq 1 ]; then timeout 600 python bench.py --gpus 1 --config $C --steps $K --warmup $W "$@" > $O/scale_${C}_n$N.json 2> $O/scale_${C}_n$N.err
