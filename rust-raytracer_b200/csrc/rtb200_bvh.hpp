@@ -201,26 +201,36 @@ private:
         constexpr int NB = 16;
         double best = INFINITY; int best_axis = -1, best_bin = -1;
         if (depth < sah_limit_) {
+            // one pass over the primitives fills the bins of all three axes
+            Box bb[3][NB]; uint32_t bc[3][NB] = {{0}};
+            double lo3[3], scale3[3]; bool use[3];
             for (int a = 0; a < 3; ++a) {
-                const double lo = cbox.lo[a], ext = cbox.hi[a] - cbox.lo[a];
-                if (!(ext > 0)) continue;
-                Box bb[NB]; uint32_t bc[NB] = {0};
-                for (uint32_t t = first; t < first + count; ++t) {
-                    const uint32_t p = order_[t];
-                    int b = (int)((coord(p, a) - lo) / ext * NB);
-                    b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                    bb[b].grow(prim_box_[p]); ++bc[b];
+                const double ext = cbox.hi[a] - cbox.lo[a];
+                use[a] = ext > 0; lo3[a] = cbox.lo[a]; scale3[a] = use[a] ? ext : 1.0;
+            }
+            for (uint32_t t = first; t < first + count; ++t) {
+                const uint32_t p = order_[t];
+                const Box& pb = prim_box_[p];
+                const double c[3] = {prim_c_[p].x, prim_c_[p].y, prim_c_[p].z};
+                for (int a = 0; a < 3; ++a) {
+                    if (!use[a]) continue;
+                    int bi = (int)((c[a] - lo3[a]) / scale3[a] * NB);
+                    bi = bi < 0 ? 0 : (bi >= NB ? NB - 1 : bi);
+                    bb[a][bi].grow(pb); ++bc[a][bi];
                 }
+            }
+            for (int a = 0; a < 3; ++a) {
+                if (!use[a]) continue;
                 double ra[NB]; uint32_t rc[NB];
                 Box acc; uint32_t cnt = 0;
-                for (int b = NB - 1; b > 0; --b) { acc.grow(bb[b]); cnt += bc[b]; ra[b] = acc.area(); rc[b] = cnt; }
+                for (int bi = NB - 1; bi > 0; --bi) { acc.grow(bb[a][bi]); cnt += bc[a][bi]; ra[bi] = acc.area(); rc[bi] = cnt; }
                 acc = Box(); cnt = 0;
-                for (int b = 0; b + 1 < NB; ++b) {
-                    acc.grow(bb[b]); cnt += bc[b];
-                    if (cnt == 0 || rc[b + 1] == 0) continue;
+                for (int bi = 0; bi + 1 < NB; ++bi) {
+                    acc.grow(bb[a][bi]); cnt += bc[a][bi];
+                    if (cnt == 0 || rc[bi + 1] == 0) continue;
                     // leaves hold kLeafK slots: cost counts slot blocks, which favours full leaves
-                    const double cost = acc.area() * std::ceil(cnt / (double)kLeafK) + ra[b + 1] * std::ceil(rc[b + 1] / (double)kLeafK);
-                    if (cost < best) { best = cost; best_axis = a; best_bin = b; }
+                    const double cost = acc.area() * std::ceil(cnt / (double)kLeafK) + ra[bi + 1] * std::ceil(rc[bi + 1] / (double)kLeafK);
+                    if (cost < best) { best = cost; best_axis = a; best_bin = bi; }
                 }
             }
         }
@@ -256,12 +266,13 @@ private:
         float* rec = &R_.leaf_rec[(size_t)leaf * kLeafK * 4];
         uint32_t* ids = &R_.leaf_id[(size_t)leaf * kLeafK];
         // members in increasing ORIGINAL index (not required for correctness; keeps the layout deterministic)
-        std::vector<uint32_t> mem;
-        for (uint32_t t = b.first; t < b.first + b.count; ++t) mem.push_back(prim_id_[order_[t]]);
-        std::sort(mem.begin(), mem.end());
+        uint32_t mem[kLeafK];
+        const int n_mem = (int)b.count;
+        for (int t = 0; t < n_mem; ++t) mem[t] = prim_id_[order_[b.first + (uint32_t)t]];
+        std::sort(mem, mem + n_mem);
         for (int j = 0; j < kLeafK; ++j) {
             float r4[4] = {0.f, 0.f, 0.f, -INFINITY};   // padding slot: never hit
-            if (j < (int)mem.size()) {
+            if (j < n_mem) {
                 const rt_sphere& sp = s_->spheres[mem[j]];
                 if (!sphere_record(sp.center.x - R_.g[0], sp.center.y - R_.g[1], sp.center.z - R_.g[2], sp.radius * sp.radius, r4)) {
                     r4[0] = r4[1] = r4[2] = 0.f; r4[3] = INFINITY;

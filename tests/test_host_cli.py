@@ -102,6 +102,24 @@ def test_cli_renders_the_same_png_as_the_python_host(tmp_path, which):
     assert png.shape == (cfg["height"], cfg["width"], 3) and np.array_equal(png, ref)
 
 
+@pytest.mark.gpu
+def test_cli_on_all_gpus_writes_the_same_png_as_on_one(tmp_path):
+    """`RTB200_GPUS=0 raytracer scene.json out.png` (every GPU of the box through rtb200_render_rgb8_multi) must write the
+    same image as the single-GPU run. Skips below 2 GPUs."""
+    from PIL import Image
+    if R.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cfg = scenes._variant(scenes.cover_config(), 160, 120, 8, 50)
+    p = tmp_path / "scene.json"; p.write_text(json.dumps(cfg))
+    one, many = tmp_path / "one.png", tmp_path / "all.png"
+    r1 = _run([str(p), str(one)], cwd=scenes.SCENES_DIR)
+    env = dict(os.environ, RTB200_GPUS="0", RTB200_STATS="1")
+    r2 = subprocess.run([CLI, str(p), str(many)], capture_output=True, text=True, cwd=scenes.SCENES_DIR, env=env)
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    assert f"gpus={R.device_count()}" in r2.stderr
+    assert np.array_equal(np.asarray(Image.open(one)), np.asarray(Image.open(many)))
+
+
 def test_jpeg_decoder_survives_malformed_headers(tmp_path):
     """load_texture_image runs on scene-named files: malformed segments must produce an error (the reference's jpeg-decoder
     crate returns Err and the caller panics cleanly), never an out-of-bounds read. Mutates the header bytes of a small
