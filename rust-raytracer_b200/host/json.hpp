@@ -41,7 +41,9 @@ class JsonParser {
             case 'b': s += '\b'; break; case 'f': s += '\f'; break; case 'u': { if (e - p < 5) err("bad \\u"); unsigned cp = (unsigned)std::strtoul(std::string(p + 1, 4).c_str(), nullptr, 16); p += 4;
                 if (cp < 0x80) s += (char)cp; else if (cp < 0x800) { s += (char)(0xC0 | (cp >> 6)); s += (char)(0x80 | (cp & 63)); } else { s += (char)(0xE0 | (cp >> 12)); s += (char)(0x80 | ((cp >> 6) & 63)); s += (char)(0x80 | (cp & 63)); } break; }
             default: s += *p; } ++p; } else s += *p++; }
-        if (p >= e) err("unterminated string"); ++p; return s; }
+        if (p >= e) { err("unterminated string"); }
+        ++p;
+        return s; }
 public:
     static Json parse(const std::string& text) { JsonParser q; q.p = text.data(); q.e = q.p + text.size(); Json j = q.value(); q.ws(); if (q.p != q.e) q.err("trailing characters"); return j; }
 };

@@ -89,14 +89,17 @@ class DistributedRenderer:
         self.resident = ResidentScene(scene, self.opts)
         self.rows = self.resident.rows
         self.rows_max = padded_rows(self.h, self.world, band_rows)
-        self.shards = [torch.zeros((self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        # a ring of shard buffers deeper than the two frames in flight: frame k+2 does not have to wait for the gather of frame k
+        # (which ends only when the SLOWEST rank has delivered frame k), so rank-to-rank jitter of up to two frames is absorbed
+        self.n_shards = 4
+        self.shards = [torch.zeros((self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(self.n_shards)]
         self.shard = self.shards[0]
         self.frame = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device) if self.rank == 0 else None
         self.gbuf = torch.empty((self.world, self.rows_max, self.w, 3), dtype=torch.uint8, device=self.device) if (self.rank == 0 and self.world > 1) else None
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self.frame_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]   # consecutive frames alternate streams
-        self._traced = [torch.cuda.Event() for _ in range(2)]     # shard k has been written by resolve
-        self._gathered = [torch.cuda.Event() for _ in range(2)]   # shard k has been consumed by the gather
+        self._traced = [torch.cuda.Event() for _ in range(self.n_shards)]     # shard k has been written by resolve
+        self._gathered = [torch.cuda.Event() for _ in range(self.n_shards)]   # shard k has been consumed by the gather
         self._frame_no = 0
 
     def render(self) -> dict:
@@ -113,14 +116,14 @@ class DistributedRenderer:
         """Enqueue one frame without waiting. Frames alternate between two streams (and two shard buffers, and the
         library's two work-buffer sets), so frame k+1 starts tracing while frame k drains its last paths, resolves and
         is gathered on the side stream."""
-        k = self._frame_no & 1
+        k = self._frame_no % self.n_shards
+        fs = self.frame_streams[self._frame_no & 1]
         self._frame_no += 1
         cur = torch.cuda.current_stream()
-        fs = self.frame_streams[k]
         fs.wait_stream(cur)                                      # whatever the caller enqueued before this frame
         shard = self.shards[k]
-        if self.world > 1 and self._frame_no > 2:
-            fs.wait_event(self._gathered[k])                    # the gather two frames ago has finished reading this shard
+        if self.world > 1 and self._frame_no > self.n_shards:
+            fs.wait_event(self._gathered[k])                    # the gather n_shards frames ago has finished reading this shard
         self.resident.render_async(shard.data_ptr(), 0, fs.cuda_stream)
         self.shard = shard
         if self.world > 1:
