@@ -18,6 +18,7 @@ using namespace rtk;
 
 static_assert(sizeof(rtbvh::Mat32) == sizeof(DevMat), "host and device material records must agree");
 static_assert(rtbvh::kLeafK == kLeafK && rtbvh::kNodeFloats == kNodeVec * 4, "host and device BVH layouts must agree");
+static_assert(kCapIn >= 32 + 7 * rtbvh::kMaxDepth + 8, "the node stack must hold 32 roots plus a single-entry descent of the deepest tree (LIFO reserve, DESIGN.md 4.1)");
 
 namespace {
 

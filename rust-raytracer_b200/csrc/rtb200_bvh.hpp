@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,7 +36,8 @@ constexpr int kWide = 8;          // children per node
 constexpr int kNodeFloats = 56;   // lo_x[8] lo_y[8] lo_z[8] hi_x[8] hi_y[8] hi_z[8] child[8]  (224 bytes)
 constexpr uint32_t kEmptyChild = 0xffffffffu;
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr int kMaxDepth = 32;     // wide levels; the kernel's traversal stack reserve is 7*depth + 8 entries
+constexpr int kMaxDepth = 21;     // wide levels the builder can produce; the kernel's node stack needs 32 + 7*depth + 8 entries (rtb200_api.cu asserts it)
+constexpr int kAreaFirstLevels = 15;   // below this wide level children are expanded breadth-first (3 binary levels per wide level)
 constexpr double kU = 5.9604644775390625e-8;   // 2^-24
 
 struct Mat32 { float r, g, b; uint32_t kind; double param; int32_t tex; int32_t pad; };   // = rtk::DevMat
@@ -122,6 +124,7 @@ public:
         int lg = 0;
         while (((size_t)kLeafK << lg) < order_.size()) ++lg;
         sah_limit_ = std::max(4, 30 - lg - 1);
+        if (const char* e = getenv("RTB200_BVH_AREA_LEVELS")) area_levels_ = std::max(1, atoi(e));   // test hook: exercise the breadth-first collapse
         const int root = build(0, (uint32_t)order_.size(), 0);
         R_.depth = 0;
         emit_wide(root, 1);
@@ -139,6 +142,7 @@ private:
     std::vector<uint32_t> order_;
     std::vector<BinNode> bin_;
     int sah_limit_ = 24;
+    int area_levels_ = kAreaFirstLevels;
 
     void recentre() {
         const uint32_t n = R_.n;
@@ -293,7 +297,21 @@ private:
         std::vector<int> kids;
         if (bin_[b].left < 0) kids.push_back(b);   // the whole tree is one leaf
         else { kids.push_back(bin_[b].left); kids.push_back(bin_[b].right); }
-        while ((int)kids.size() < kWide) {
+        // Largest-area-first expansion gives the tightest nodes but only guarantees ONE binary level per wide level on a path.
+        // From wide level kAreaFirstLevels on, every inner child is expanded twice instead (2 -> 4 -> 8 children): three binary
+        // levels per wide level on every path, so with a binary depth <= 30 the wide depth is <= 15 + ceil(16/3) = 21 = kMaxDepth
+        // whatever the input (real scenes stay far below level 15: cover 3, 10 k spheres 4, 100 k spheres 6).
+        if ((int)level >= area_levels_) {
+            for (int round = 0; round < 2; ++round) {
+                std::vector<int> next;
+                for (int k : kids) {
+                    if (bin_[k].left < 0) next.push_back(k);
+                    else { next.push_back(bin_[k].left); next.push_back(bin_[k].right); }
+                }
+                kids.swap(next);
+            }
+        }
+        while ((int)level < area_levels_ && (int)kids.size() < kWide) {
             int pick = -1; double pa = -1.0;
             for (int i = 0; i < (int)kids.size(); ++i) {
                 const BinNode& c = bin_[kids[i]];

@@ -193,3 +193,31 @@ def test_degenerate_inputs_build():
     assert one["n_nodes"] == 1 and one["n_leaves"] == 1 and one["depth"] == 1
     none = R.bvh_records(R.Scene.from_config(base_config(8, 6, 1, 2, [])))
     assert none["n_nodes"] == 0 and none["n_leaves"] == 0
+
+
+def test_breadth_first_collapse_is_sound_and_bounds_the_depth(monkeypatch):
+    """Below wide level 15 the builder expands every inner child twice (three binary levels per wide level), which bounds the
+    wide depth by 21 for any input; real scenes never get there, so the test hook RTB200_BVH_AREA_LEVELS=1 forces that collapse
+    from the root: the tree must still hold every sphere once, bound its members, and the emulated traversal must still reach
+    every sphere the exact test accepts."""
+    monkeypatch.setenv("RTB200_BVH_AREA_LEVELS", "1")
+    sc = R.Scene.from_config(scenes._variant(scenes.rtiow_config(20), 32, 24, 1, 4))
+    b = R.bvh_records(sc)
+    monkeypatch.delenv("RTB200_BVH_AREA_LEVELS")
+    ref = R.bvh_records(sc)
+    assert b["depth"] <= 21 and b["n_leaves"] == ref["n_leaves"] and b["n_nodes"] != ref["n_nodes"]
+    ids = b["leaf_id"].ravel()
+    assert sorted(ids[ids != EMPTY].tolist()) == list(range(sc.n_spheres))
+    c, r = _spheres(sc)
+    rng = np.random.default_rng(3)
+    cam = np.array([sc.c.camera.origin.x, sc.c.camera.origin.y, sc.c.camera.origin.z])
+    n_exact = 0
+    for i in range(150):
+        j = int(rng.integers(len(r)))
+        o = cam if i % 3 == 0 else c[j] + np.array([0.0, abs(r[j]), 0.0])
+        d = (c[int(rng.integers(len(r)))] + rng.normal(size=3) * 0.3) - o
+        exact = _exact_hits(c, r, o, d)
+        cand, _ = _traverse(b, o, d)
+        assert not (set(exact.tolist()) - cand)
+        n_exact += len(exact)
+    assert n_exact > 100
