@@ -18,6 +18,8 @@
 // and ships no golden image. The oracle is pinned against every known-answer test the reference's own
 // test-suite holds for this path (tests/test_oracle_kat.py): sphere.rs:81-88, materials.rs:157-174,
 // raytracer.rs:167-189, camera.rs:87-122, ray.rs:52-63, point3d.rs:196-272, raytracer.rs:231-248.
+// A second restatement written separately (tests/py_restatement.py, pure Python) must produce the same bits
+// (tests/test_oracle_vs_python_restatement.py).
 // PARITY UNPINNED at three third-party boundaries whose crates are absent from /root/reference:
 //   rand 0.8.x      (the reference draws from an OS-seeded ThreadRng, never reproducible) — replaced by the
 //                   counter-based Philox4x32-10 stream defined below, drawn in the reference's draw ORDER;
