@@ -696,6 +696,7 @@ int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32
     const int first = base.device < 0 ? 0 : base.device;
     if (first >= count) return fail(RT_ERR_NO_DEVICE, "no such CUDA device");
     int G = n_gpus <= 0 ? count - first : std::min(n_gpus, count - first);
+    G = std::min(G, 64 - first);   // device contexts exist for ordinals below 64
     const uint32_t bands = (s->height + base.band_rows - 1) / base.band_rows;
     G = (int)std::min<uint32_t>((uint32_t)G, bands);   // a device needs at least one band
     if (G <= 1) { base.device = first; int r = render_host(s, &base, out_rgb8, nullptr, stats); if (r == RT_OK && stats) stats->gpus_used = 1; return r; }

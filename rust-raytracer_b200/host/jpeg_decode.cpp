@@ -154,6 +154,7 @@ bool decode_jpeg(const uint8_t* data, size_t size, Image* out, std::string* err)
             if (s[0] != 8) return fail("only 8-bit JPEG is supported");
             height = (s[1] << 8) | s[2]; width = (s[3] << 8) | s[4]; ncomp = s[5];
             if (width == 0 || height == 0) return fail("zero image dimension");
+            if ((size_t)width * (size_t)height > ((size_t)1 << 28)) return fail("image larger than 2^28 pixels");   // textures of this path are a few megapixels
             if (ncomp != 1 && ncomp != 3) return fail("only 1 or 3 components are supported");
             if (n < (size_t)(6 + 3 * ncomp)) return fail("truncated SOF");
             for (int c = 0; c < ncomp; ++c) {
