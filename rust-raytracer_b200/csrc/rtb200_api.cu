@@ -137,6 +137,15 @@ inline V3 vunit(V3 a) { double l = vlen(a); return V3{a.x / l, a.y / l, a.z / l}
 inline V3 vcross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 inline rt_vec3 rv(V3 a) { return rt_vec3{a.x, a.y, a.z}; }
 
+// No C++ exception may unwind through the C boundary (std::bad_alloc while building the hierarchy of a huge scene, ...).
+template <typename F>
+int guarded(F&& f) {
+    try { return f(); }
+    catch (const std::bad_alloc&) { return fail(RT_ERR_OOM, "host memory allocation failed"); }
+    catch (const std::exception& e) { return fail(RT_ERR_INVALID, std::string("internal error: ") + e.what()); }
+    catch (...) { return fail(RT_ERR_INVALID, "internal error: unknown exception"); }
+}
+
 uint32_t mode_of(uint32_t variant) {
     return variant == RT_VARIANT_EXACT_F64 ? MODE_EXACT : (variant == RT_VARIANT_BRUTE_FORCE ? MODE_BRUTE : MODE_TREE);
 }
@@ -221,6 +230,7 @@ static int render_collect(rtb200_scene_handle h, rt_stats* stats);
 int rtb200_debug_bvh(const rt_scene* s, double recentre[3], uint32_t info[8], float* nodes, uint64_t cap_nodes, float* leaf_rec,
                      uint64_t cap_leaf_rec, uint32_t* leaf_id, uint64_t cap_leaf_id, uint32_t* always, uint64_t cap_always,
                      float* flat, uint64_t cap_flat) {
+  return guarded([&]() -> int {
     if (!s || !info) return fail(RT_ERR_INVALID, "null argument");
     if (s->n_spheres >= (1ull << 26)) return fail(RT_ERR_UNSUPPORTED, "2^26 or more spheres (list entries carry 27-bit ids)");
     if (s->n_spheres && !s->spheres) return fail(RT_ERR_INVALID, "spheres is null");
@@ -235,6 +245,7 @@ int rtb200_debug_bvh(const rt_scene* s, double recentre[3], uint32_t info[8], fl
     if (always) memcpy(always, R.always.data(), std::min<uint64_t>(cap_always, R.always.size()) * 4);
     if (flat) memcpy(flat, R.flat.data(), std::min<uint64_t>(cap_flat, R.flat.size()) * 4);
     return RT_OK;
+  });
 }
 
 int rtb200_scene_release(rtb200_scene_handle h) {
@@ -450,6 +461,7 @@ static int scene_upload_records(const rt_scene* s, const rt_options& opts, uint3
 }
 
 int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_scene_handle* out) {
+  return guarded([&]() -> int {
     if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
     *out = nullptr;
     rt_options opts;
@@ -461,6 +473,7 @@ int rtb200_scene_upload(const rt_scene* s, const rt_options* opts_in, rtb200_sce
     rtbvh::Records R;
     rtbvh::build_records(s, mode_of(opts.variant) == MODE_TREE, R);
     return scene_upload_records(s, opts, n_lights, R, out);
+  });
 }
 
 int rtb200_scene_kernel_info(rtb200_scene_handle h, rt_kernel_info* out) {
@@ -667,11 +680,11 @@ static int render_host(const rt_scene* s, const rt_options* opts, uint8_t* out_r
 
 int rtb200_render_rgb8(const rt_scene* scene, const rt_options* opts, uint8_t* out_rgb8, rt_stats* stats) {
     if (!scene || !out_rgb8) return fail(RT_ERR_INVALID, "null argument");
-    return render_host(scene, opts, out_rgb8, nullptr, stats);
+    return guarded([&]() -> int { return render_host(scene, opts, out_rgb8, nullptr, stats); });
 }
 int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, float* out_rgb, rt_stats* stats) {
     if (!scene || !out_rgb) return fail(RT_ERR_INVALID, "null argument");
-    return render_host(scene, opts, nullptr, out_rgb, stats);
+    return guarded([&]() -> int { return render_host(scene, opts, nullptr, out_rgb, stats); });
 }
 
 // One process, n_gpus devices: the reference's row bands (raytracer.rs:254-262) dealt round-robin to the devices (band b ->
@@ -681,6 +694,7 @@ int rtb200_render_linear_f32(const rt_scene* scene, const rt_options* opts, floa
 static std::mutex g_multi_mu;   // multi-GPU calls take turns (they share the frame buffer of the first device)
 
 int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32_t n_gpus, uint8_t* out_rgb8, rt_stats* stats) {
+  return guarded([&]() -> int {
     if (!s || !out_rgb8) return fail(RT_ERR_INVALID, "null argument");
     auto wall0 = std::chrono::steady_clock::now();
     rt_options base;
@@ -747,7 +761,7 @@ int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32
             r.h2d = h->h2d_bytes;
             return RT_OK;
         };
-        r.rc = body();
+        r.rc = guarded(body);
         if (r.rc != RT_OK) r.err = g_last_error;
     };
     std::vector<std::thread> threads;
@@ -774,6 +788,7 @@ int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32
     total.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     if (stats) *stats = total;
     return RT_OK;
+  });
 }
 
 // ---- probes ------------------------------------------------------------------------------------------
