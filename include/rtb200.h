@@ -13,7 +13,8 @@
  *   - the callee copies what it needs before returning; no callee allocation escapes
  *     except opaque handles released with the matching *_release call;
  *   - every function returns 0 on success, a negative rt_status otherwise, and
- *     rtb200_last_error() then returns a thread-local message (the reference panics instead);
+ *     rtb200_last_error() then returns a thread-local message (the reference panics instead); no C++
+ *     exception leaves the library (host out-of-memory while building the hierarchy is RT_ERR_OOM);
  *   - calls are blocking unless stated otherwise. Thread safety: every device has its own execution context guarded
  *     by a mutex, so two host threads may render on two DIFFERENT devices concurrently; calls that use the same
  *     device are serialised. A scene handle must not be used from two threads at once. The caller's current CUDA
