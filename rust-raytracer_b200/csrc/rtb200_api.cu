@@ -765,9 +765,13 @@ int rtb200_render_rgb8_multi(const rt_scene* s, const rt_options* opts_in, int32
         if (r.rc != RT_OK) r.err = g_last_error;
     };
     std::vector<std::thread> threads;
-    for (int g = 1; g < G; ++g) threads.emplace_back(worker, g);
-    worker(0);
-    for (auto& t : threads) t.join();
+    threads.reserve((size_t)G);
+    struct Joiner { std::vector<std::thread>& ts; ~Joiner() { for (auto& t : ts) if (t.joinable()) t.join(); } };
+    {
+        Joiner joiner{threads};   // also on the exceptional path (thread creation can throw): never destroy a joinable thread
+        for (int g = 1; g < G; ++g) threads.emplace_back(worker, g);
+        worker(0);
+    }
     for (int g = 0; g < G; ++g) if (res[(size_t)g].rc != RT_OK) return fail(res[(size_t)g].rc, "device " + std::to_string(first + g) + ": " + res[(size_t)g].err);
     rt_stats total{};
     for (int g = 0; g < G; ++g) {
