@@ -20,10 +20,13 @@ struct Json {
 };
 class JsonParser {
     const char* p; const char* e;
+    int depth = 0;                              // serde_json's default recursion limit is 128 ("recursion limit exceeded")
+    struct Nest { JsonParser& q; explicit Nest(JsonParser& q_) : q(q_) { if (++q.depth > 128) q.err("recursion limit exceeded"); } ~Nest() { --q.depth; } };
     void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
     [[noreturn]] void err(const char* m) { throw std::runtime_error(std::string("json: ") + m); }
     Json value() {
         ws(); if (p >= e) err("unexpected end");
+        Nest nest(*this);
         Json j;
         if (*p == '{') { ++p; j.kind = Json::Obj; ws(); if (p < e && *p == '}') { ++p; return j; }
             for (;;) { ws(); if (p >= e || *p != '"') err("key expected"); std::string k = str(); ws(); if (p >= e || *p != ':') err("':' expected"); ++p;
