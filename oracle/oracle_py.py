@@ -17,7 +17,8 @@ _REPO = os.path.dirname(_HERE)
 sys.path.insert(0, os.path.join(_REPO, "rust-raytracer_b200"))
 import rtb200 as R  # struct definitions (include/rtb200.h mirrors) only  # noqa: E402
 
-LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# RTB200_ORACLE_LIB: load another build of the same sources instead (tests/test_oracle_ubsan.py loads a UBSan build)
+LIB_PATH = os.environ.get("RTB200_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
 
 
 class oracle_stats(C.Structure):
@@ -38,6 +39,8 @@ _lib = None
 
 def build(force: bool = False):
     """(Re)build liboracle.so when it is missing or older than its sources / include/rtb200.h (the structs it reads)."""
+    if os.environ.get("RTB200_ORACLE_LIB"):
+        return
     deps = [os.path.join(_HERE, f) for f in ("rt_oracle_capi.cpp", "rt_oracle.hpp", "Makefile")] + [os.path.join(_REPO, "include", "rtb200.h")]
     stale = not os.path.exists(LIB_PATH) or any(os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
